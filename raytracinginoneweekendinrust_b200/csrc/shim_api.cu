@@ -1,0 +1,338 @@
+// shim_api.cu — the C ABI (include/shimmer_b200.h): scene recording, commit/upload, the
+// wavefront driver and the gate-1 batch query.  No CPU fallback: every device entry point
+// fails with SHIM_ERR_CUDA when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "shim_internal.h"
+#include "shim_kernels.cuh"
+
+using namespace shim;
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return set_err(SHIM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t upload(const std::vector<T>& v) {
+        release();
+        n = v.size();
+        // never hand out a null pointer: empty arrays still get a valid allocation
+        cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (n) e = cudaMemcpy(p, v.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+        return e;
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        return cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct DeviceScene {
+    DevBuf<DevNode> nodes;
+    DevBuf<double> sph;
+    DevBuf<f4> sph_s, msph, rect, tri, cube, materials, textures;
+    DevBuf<int> sph_mat;
+    DevBuf<DevObject> objects;
+    DevBuf<uint8_t> images, perlin;
+    DevBuf<int> handle[5];
+    SceneView view;
+    uint64_t bytes = 0;
+    void release() {
+        nodes.release(); sph.release(); sph_s.release(); msph.release(); rect.release(); tri.release(); cube.release();
+        materials.release(); textures.release(); sph_mat.release(); objects.release(); images.release(); perlin.release();
+        for (auto& h : handle) h.release();
+    }
+};
+
+struct Wavefront {
+    uint32_t pool = 0;
+    DevBuf<f4> ray_o[2], ray_d[2], thr[2], hit;
+    DevBuf<uint32_t> samp[2], mq[MAT_KINDS], cnt;
+    DevBuf<float> accum;
+    DevBuf<uint32_t> pix_table;
+    int pt_key[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t npix = 0;
+    uint32_t* h_flags = nullptr;  // pinned: done flag readbacks
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr};
+    int grid_extend = 0, grid_shade = 0, grid_generate = 0;
+    void release() {
+        for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); samp[i].release(); }
+        hit.release(); cnt.release(); accum.release(); pix_table.release();
+        for (auto& q : mq) q.release();
+        if (h_flags) cudaFreeHost(h_flags);
+        h_flags = nullptr;
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (auto& e : ev_chunk) if (e) cudaEventDestroy(e);
+        ev0 = ev1 = ev_chunk[0] = ev_chunk[1] = nullptr;
+        pool = 0;
+    }
+};
+
+}  // namespace
+
+struct shim::DeviceState {
+    DeviceScene scene;
+    Wavefront wf;
+    int device = -1;
+    int sm_count = 0;
+};
+void shim::device_state_release(DeviceState* d) {
+    if (!d) return;
+    d->scene.release();
+    d->wf.release();
+    delete d;
+}
+
+// ------------------------------------------------------------------------------------------ commit
+static int ensure_device(shim_scene* s) {
+    if (!s->dev) s->dev = new DeviceState();
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_err(SHIM_ERR_CUDA, std::string("no usable CUDA device (this backend has no CPU fallback): ") +
+                                          (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    CU(cudaGetDevice(&s->dev->device));
+    CU(cudaDeviceGetAttribute(&s->dev->sm_count, cudaDevAttrMultiProcessorCount, s->dev->device));
+    return SHIM_OK;
+}
+
+SHIM_API int shim_commit(shim_scene* s) {
+    MUTABLE(s);
+    int rc = s->sb.flatten(s->flat);
+    if (rc < 0) return set_err(rc, s->sb.err);
+    if (s->flat.objects.size() > 65535) return set_err(SHIM_ERR_UNSUPPORTED, "more than 65535 top-level objects");
+    rc = ensure_device(s);
+    if (rc < 0) return rc;
+    const FlatScene& f = s->flat;
+    DeviceScene& d = s->dev->scene;
+    CU(d.nodes.upload(f.nodes)); CU(d.sph.upload(f.sph)); CU(d.sph_s.upload(f.sph_s)); CU(d.sph_mat.upload(f.sph_mat));
+    CU(d.msph.upload(f.msph)); CU(d.rect.upload(f.rect)); CU(d.tri.upload(f.tri)); CU(d.cube.upload(f.cube));
+    CU(d.objects.upload(f.objects)); CU(d.materials.upload(f.materials)); CU(d.textures.upload(f.textures));
+    CU(d.images.upload(f.images)); CU(d.perlin.upload(f.perlin));
+    for (int i = 0; i < 5; ++i) CU(d.handle[i].upload(f.handle[i]));
+    SceneView& v = d.view;
+    memset(&v, 0, sizeof v);
+    v.nodes = d.nodes.p; v.sph = d.sph.p; v.sph_s = d.sph_s.p; v.sph_mat = d.sph_mat.p; v.msph = d.msph.p; v.rect = d.rect.p;
+    v.tri = d.tri.p; v.cube = d.cube.p; v.objects = d.objects.p; v.materials = d.materials.p; v.textures = d.textures.p;
+    v.images = d.images.p; v.perlin = d.perlin.p;
+    for (int i = 0; i < 5; ++i) v.handle[i] = d.handle[i].p;
+    v.n_objects = (int)f.objects.size(); v.n_nodes = (int)f.nodes.size();
+    d.bytes = f.bytes();
+    s->has_media = false;
+    for (const DevObject& o : f.objects) if (o.flags & OBJ_MEDIUM) s->has_media = true;
+    s->committed = true;
+    return SHIM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ render
+static int wf_prepare(shim_scene* s, const shim_render_params& p) {
+    Wavefront& w = s->dev->wf;
+    uint32_t pool = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 21);
+    const char* env = getenv("SHIM_POOL_PATHS");
+    if (p.pool_paths <= 0 && env && atoi(env) > 0) pool = (uint32_t)atoi(env);
+    pool = (pool + 31u) & ~31u;
+    if (w.pool != pool) {
+        for (int i = 0; i < 2; ++i) { CU(w.ray_o[i].alloc(pool)); CU(w.ray_d[i].alloc(pool)); CU(w.thr[i].alloc(pool)); CU(w.samp[i].alloc(pool)); }
+        CU(w.hit.alloc(pool));
+        for (int k = 0; k < MAT_KINDS; ++k) CU(w.mq[k].alloc(pool));
+        CU(w.cnt.alloc(CNT_WORDS));
+        if (!w.h_flags) CU(cudaMallocHost(&w.h_flags, 64 * sizeof(uint32_t)));
+        if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); CU(cudaEventCreate(&w.ev_chunk[0])); CU(cudaEventCreate(&w.ev_chunk[1])); }
+        w.pool = pool;
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_extend, 256, 0));
+        w.grid_extend = s->dev->sm_count * (per_sm > 0 ? per_sm : 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_shade<MAT_LAMBERTIAN>, 256, 0));
+        w.grid_shade = s->dev->sm_count * (per_sm > 0 ? per_sm : 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
+        w.grid_generate = s->dev->sm_count * (per_sm > 0 ? per_sm : 1);
+    }
+    size_t fb = (size_t)p.width * p.height * 3;
+    if (w.accum.n != fb) CU(w.accum.alloc(fb));
+    int world = p.tile_world > 1 ? p.tile_world : 1;
+    int key[6] = {p.width, p.height, p.tile_width, p.tile_height, world > 1 ? p.tile_rank : 0, world};
+    if (memcmp(key, w.pt_key, sizeof key) != 0) {
+        std::vector<uint32_t> order = tile_pixel_order(p.width, p.height, p.tile_width, p.tile_height, key[4], world);
+        CU(w.pix_table.upload(order));
+        w.npix = (uint32_t)order.size();
+        memcpy(w.pt_key, key, sizeof key);
+    }
+    return SHIM_OK;
+}
+
+SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shim_render_params* pp, float* d_out, shim_stats* stats,
+                                void* cuda_stream) {
+    NEED(s);
+    if (!s->committed) return set_err(SHIM_ERR_STATE, "shim_render: scene not committed");
+    if (!cam || !pp || !d_out) return set_err(SHIM_ERR_INVALID, "shim_render: null argument");
+    const shim_render_params& p = *pp;
+    if (p.width < 2 || p.height < 2 || p.samples_per_pixel < 1 || p.tile_width < 1 || p.tile_height < 1 || p.max_depth < 0 ||
+        p.sample_count < 0 || p.sample_begin < 0 || (p.tile_world > 1 && (p.tile_rank < 0 || p.tile_rank >= p.tile_world)))
+        return set_err(SHIM_ERR_INVALID, "shim_render: bad render params");
+    if ((uint64_t)p.width * (uint64_t)p.height > 0x7fffffffull) return set_err(SHIM_ERR_INVALID, "shim_render: image too large");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = wf_prepare(s, p);
+    if (rc < 0) return rc;
+    Wavefront& w = s->dev->wf;
+
+    WfParams k;
+    memset(&k, 0, sizeof k);
+    k.sv = s->dev->scene.view;
+    camera_new(cam->look_from, cam->look_at, cam->view_up, cam->vertical_fov, cam->aspect_ratio, cam->aperture, cam->focus_dist,
+               cam->time_start, cam->time_end, k.cam);
+    for (int i = 0; i < 2; ++i) { k.ray_o[i] = w.ray_o[i].p; k.ray_d[i] = w.ray_d[i].p; k.thr[i] = w.thr[i].p; k.samp[i] = w.samp[i].p; }
+    k.hit = w.hit.p;
+    for (int q = 0; q < MAT_KINDS; ++q) k.mq[q] = w.mq[q].p;
+    k.cnt = w.cnt.p; k.accum = w.accum.p; k.pix_table = w.pix_table.p;
+    k.npix = w.npix;
+    int count = p.sample_count > 0 ? p.sample_count : p.samples_per_pixel;
+    k.total_samples = (uint64_t)w.npix * (uint64_t)count;
+    k.pool = w.pool; k.width = p.width; k.height = p.height; k.max_depth = p.max_depth; k.sample_begin = p.sample_begin;
+    k.bg[0] = p.background[0]; k.bg[1] = p.background[1]; k.bg[2] = p.background[2];
+    k.seed = p.seed; k.has_media = s->has_media ? 1 : 0; k.count_nodes = (p.flags & SHIM_RENDER_COUNT_NODES) ? 1 : 0;
+
+    CU(cudaMemsetAsync(w.cnt.p, 0, CNT_WORDS * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(w.accum.p, 0, w.accum.n * sizeof(float), st));
+    CU(cudaEventRecord(w.ev0, st));
+
+    uint64_t launches = 0;
+    if (k.total_samples > 0 && p.max_depth > 0) {
+        // iterations are enqueued in chunks; the done flag of chunk c is read back while chunk c+1 runs
+        const int chunk = 8;
+        int cur = 0, pending = -1;
+        bool done = false;
+        for (int c = 0; !done; ++c) {
+            for (int it = 0; it < chunk; ++it) {
+                wf_begin<<<1, 32, 0, st>>>(k, cur);
+                wf_generate<<<w.grid_generate, 256, 0, st>>>(k, cur);
+                wf_extend<<<w.grid_extend, 256, 0, st>>>(k, cur);
+                wf_shade<MAT_LAMBERTIAN><<<w.grid_shade, 256, 0, st>>>(k, cur);
+                wf_shade<MAT_METAL><<<w.grid_shade, 256, 0, st>>>(k, cur);
+                wf_shade<MAT_DIELECTRIC><<<w.grid_shade, 256, 0, st>>>(k, cur);
+                wf_shade<MAT_DIFFUSE_LIGHT><<<w.grid_shade, 256, 0, st>>>(k, cur);
+                wf_shade<MAT_ISOTROPIC><<<w.grid_shade, 256, 0, st>>>(k, cur);
+                launches += 8;
+                cur = 1 - cur;
+            }
+            int slot = c & 1;
+            CU(cudaMemcpyAsync(w.h_flags + 16 * slot, w.cnt.p + CNT_DONE, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(w.ev_chunk[slot], st));
+            if (pending >= 0) {
+                CU(cudaEventSynchronize(w.ev_chunk[pending]));
+                if (w.h_flags[16 * pending]) done = true;
+            }
+            pending = slot;
+            if (c > (1 << 24)) return set_err(SHIM_ERR_CUDA, "wavefront did not terminate");
+        }
+    }
+    size_t fb = (size_t)p.width * p.height * 3;
+    wf_finalize<<<s->dev->sm_count * 4, 256, 0, st>>>(w.accum.p, d_out, fb, (float)p.samples_per_pixel, (p.flags & SHIM_RENDER_RAW_SUM) ? 1 : 0);
+    launches += 1;
+    CU(cudaEventRecord(w.ev1, st));
+    CU(cudaMemcpyAsync(w.h_flags + 32, w.cnt.p, CNT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        const uint64_t* c64 = reinterpret_cast<const uint64_t*>(w.h_flags + 32 + CNT_U64_BASE);
+        stats->rays = c64[C64_RAYS];
+        stats->samples = k.total_samples;
+        stats->node_visits = c64[C64_NODES];
+        stats->prim_tests = c64[C64_PRIMS];
+        stats->kernel_launches = launches;
+        stats->iterations = w.h_flags[32 + CNT_ITER];
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
+        stats->device_ms = ms;
+    }
+    return SHIM_OK;
+}
+
+SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_render_params* p, float* out, shim_stats* stats) {
+    NEED(s);
+    if (!p || !out) return set_err(SHIM_ERR_INVALID, "shim_render: null argument");
+    if (!s->committed) return set_err(SHIM_ERR_STATE, "shim_render: scene not committed");
+    if (p->width < 2 || p->height < 2) return set_err(SHIM_ERR_INVALID, "shim_render: bad render params");
+    size_t fb = (size_t)p->width * p->height * 3;
+    float* d_out = nullptr;
+    CU(cudaMalloc(&d_out, fb * sizeof(float)));
+    int rc = shim_render_device(s, cam, p, d_out, stats, nullptr);
+    if (rc == SHIM_OK) {
+        cudaError_t e = cudaMemcpy(out, d_out, fb * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_err(SHIM_ERR_CUDA, std::string("framebuffer copy: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ gate 1
+SHIM_API int shim_trace_closest_device(shim_scene* s, const float* d_rays, int64_t n, float t_min, float t_max, uint64_t seed,
+                                       int32_t* d_prim, float* d_t, void* cuda_stream) {
+    NEED(s);
+    if (!s->committed) return set_err(SHIM_ERR_STATE, "shim_trace_closest: scene not committed");
+    if (n < 0 || (n > 0 && (!d_rays || !d_prim || !d_t))) return set_err(SHIM_ERR_INVALID, "shim_trace_closest: bad arguments");
+    if (n == 0) return SHIM_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int grid = (int)((n + 255) / 256);
+    int cap = s->dev->sm_count * 8;
+    if (grid > cap) grid = cap;
+    trace_closest_kernel<<<grid, 256, 0, st>>>(s->dev->scene.view, d_rays, (long long)n, t_min, t_max, seed, d_prim, d_t, nullptr);
+    CU(cudaGetLastError());
+    return SHIM_OK;
+}
+
+SHIM_API int shim_trace_closest(shim_scene* s, const float* rays, int64_t n, float t_min, float t_max, uint64_t seed, int32_t* prim,
+                                float* t, uint64_t* counters) {
+    NEED(s);
+    if (!s->committed) return set_err(SHIM_ERR_STATE, "shim_trace_closest: scene not committed");
+    if (n < 0 || (n > 0 && (!rays || !prim || !t))) return set_err(SHIM_ERR_INVALID, "shim_trace_closest: bad arguments");
+    if (n == 0) { if (counters) counters[0] = counters[1] = counters[2] = 0; return SHIM_OK; }
+    float* d_rays = nullptr; int32_t* d_prim = nullptr; float* d_t = nullptr; unsigned long long* d_cnt = nullptr;
+    int rc = SHIM_OK;
+    auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_prim); cudaFree(d_t); cudaFree(d_cnt); };
+#define CUX(call)                                                                                                     \
+    do {                                                                                                              \
+        cudaError_t e_ = (call);                                                                                      \
+        if (e_ != cudaSuccess) { cleanup(); return set_err(SHIM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } \
+    } while (0)
+    CUX(cudaMalloc(&d_rays, (size_t)n * 7 * sizeof(float)));
+    CUX(cudaMalloc(&d_prim, (size_t)n * sizeof(int32_t)));
+    CUX(cudaMalloc(&d_t, (size_t)n * sizeof(float)));
+    CUX(cudaMalloc(&d_cnt, 3 * sizeof(unsigned long long)));
+    CUX(cudaMemset(d_cnt, 0, 3 * sizeof(unsigned long long)));
+    CUX(cudaMemcpy(d_rays, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice));
+    int grid = (int)((n + 255) / 256);
+    int cap = s->dev->sm_count * 8;
+    if (grid > cap) grid = cap;
+    trace_closest_kernel<<<grid, 256>>>(s->dev->scene.view, d_rays, (long long)n, t_min, t_max, seed, d_prim, d_t, counters ? d_cnt : nullptr);
+    CUX(cudaGetLastError());
+    CUX(cudaMemcpy(prim, d_prim, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUX(cudaMemcpy(t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (counters) {
+        unsigned long long h[3];
+        CUX(cudaMemcpy(h, d_cnt, sizeof h, cudaMemcpyDeviceToHost));
+        counters[0] = (uint64_t)n; counters[1] = h[1]; counters[2] = h[2];
+    }
+    cleanup();
+    return rc;
+}
+

@@ -1,0 +1,649 @@
+// shim_device.h — the hot path's arithmetic: intersection, traversal, hit reconstruction,
+// textures and scatter.  Every function is __host__ __device__ so that tests/hostsim can
+// run the very same code on the CPU against the oracle (a test harness, never a product
+// path: the library itself only ever launches the sm_100a kernels in shim_kernels.cu).
+//
+// Arithmetic policy: this file is compiled with -fmad=false (nvcc) / -ffp-contract=off
+// (g++).  Primitive tests and shading follow the reference's IEEE f32/f64 operation order
+// (glam 0.22 scalar Vec3) so that they are bit-identical to rustc's output wherever only
+// + - * / sqrt are involved; BVH box tests are free to differ because the result of a
+// traversal is topology-independent (SURVEY.md §2.2 "BVH traversal").
+#pragma once
+#include <math.h>
+#include "shim_types.h"
+
+namespace shim {
+
+// ---------------------------------------------------------------------------- vec3
+SHIM_HD f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+SHIM_HD f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+SHIM_HD f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+SHIM_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+SHIM_HD f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+SHIM_HD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+SHIM_HD f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+SHIM_HD f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+SHIM_HD float dot3(f3 a, f3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+SHIM_HD f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+SHIM_HD float len3(f3 a) { return sqrtf(dot3(a, a)); }
+SHIM_HD f3 normalize3(f3 a) { return a * (1.0f / len3(a)); }
+SHIM_HD float comp(f3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+SHIM_HD f3 xyz(f4 v) { return mk3(v.x, v.y, v.z); }
+SHIM_HD bool signbit_f(float v) { return f2i(v) < 0; }
+
+#define SHIM_F32_EPS 1.1920929e-07f
+#define SHIM_PI 3.14159265358979323846f
+#if defined(__CUDA_ARCH__)
+#define SHIM_INF __int_as_float(0x7f800000)
+#else
+#define SHIM_INF INFINITY
+#endif
+
+struct Ray { f3 o, d; float time; };
+SHIM_HD f3 ray_at(const Ray& r, float t) { return r.o + t * r.d; }
+
+// ---------------------------------------------------------------------------- Philox4x32-10
+SHIM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+struct Rng {
+    uint32_t pixel, sample, dim, j, k0, k1;
+    uint32_t b0, b1, b2, b3;
+};
+SHIM_HD void rng_init(Rng& r, uint32_t pixel, uint32_t sample, uint64_t seed) {
+    r.pixel = pixel; r.sample = sample; r.dim = 0; r.j = 0;
+    r.k0 = (uint32_t)seed; r.k1 = (uint32_t)(seed >> 32);
+    r.b0 = r.b1 = r.b2 = r.b3 = 0;
+}
+SHIM_HD void rng_key(Rng& r, uint32_t bounce, uint32_t stage) { r.dim = bounce * 4u + stage; r.j = 0; }
+SHIM_HD void rng_refill(Rng& r) {
+    uint32_t c0 = r.pixel, c1 = r.sample, c2 = r.dim, c3 = r.j >> 2, k0 = r.k0, k1 = r.k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    r.b0 = c0; r.b1 = c1; r.b2 = c2; r.b3 = c3;
+}
+SHIM_HD uint32_t rng_u32(Rng& r) {
+    uint32_t lane = r.j & 3u;
+    if (lane == 0) rng_refill(r);
+    r.j++;
+    return lane == 0 ? r.b0 : (lane == 1 ? r.b1 : (lane == 2 ? r.b2 : r.b3));
+}
+// rand 0.8.5: random::<f32>() keeps 24 bits; gen_range keeps 23 and maps u*(hi-lo)+lo
+SHIM_HD float rng_uniform01(Rng& r) { return (float)(rng_u32(r) >> 8) * (1.0f / 16777216.0f); }
+SHIM_HD float rng_range(Rng& r, float lo, float hi) {
+    float s = hi - lo;
+    return (float)(rng_u32(r) >> 9) * (1.0f / 8388608.0f) * s + lo;
+}
+// utils.rs:9-17
+SHIM_HD f3 random_in_unit_disk(Rng& r) {
+    for (;;) {
+        float a = rng_range(r, -1.0f, 1.0f);
+        float b = rng_range(r, -1.0f, 1.0f);
+        f3 p = mk3(a, b, 0.0f);
+        if (dot3(p, p) < 1.0f) return p;
+    }
+}
+// materials/utils.rs:6-19
+SHIM_HD f3 random_in_unit_sphere(Rng& r) {
+    for (;;) {
+        float a = rng_range(r, -1.0f, 1.0f);
+        float b = rng_range(r, -1.0f, 1.0f);
+        float c = rng_range(r, -1.0f, 1.0f);
+        f3 p = mk3(a, b, c);
+        if (dot3(p, p) < 1.0f) return p;
+    }
+}
+
+// ---------------------------------------------------------------------------- camera.rs:96-106
+SHIM_HD Ray camera_get_ray(const CameraPod& c, float s, float t, Rng& rng) {
+    f3 rd = c.lens_radius * random_in_unit_disk(rng);
+    f3 offset = c.u * rd.x + c.v * rd.y;
+    float time = rng_range(rng, c.time0, c.time1);
+    Ray r;
+    r.o = c.origin + offset;
+    r.d = c.llc + s * c.horizontal + t * c.vertical - c.origin - offset;
+    r.time = time;
+    return r;
+}
+// renderer.rs:141-143
+SHIM_HD Ray camera_sample(const CameraPod& c, int x, int y, int width, int height, Rng& rng) {
+    float u = ((float)x + rng_uniform01(rng)) / (float)(width - 1);
+    float v = ((float)y + rng_uniform01(rng)) / (float)(height - 1);
+    return camera_get_ray(c, u, v, rng);
+}
+
+// ---------------------------------------------------------------------------- object-space ray
+struct RayCtx {
+    Ray r;            // ray as the shape sees it (after Translate / RotateY, instance.rs)
+    f3 inv_d;
+    double ox, oy, oz, dx, dy, dz, a;  // f64 copy for Sphere::hit
+};
+SHIM_HD f3 rot_y(f3 v, float s, float c) { return mk3(c * v.x - s * v.z, v.y, s * v.x + c * v.z); }       // instance.rs:104-110
+SHIM_HD f3 rot_y_back(f3 v, float s, float c) { return mk3(c * v.x + s * v.z, v.y, -s * v.x + c * v.z); } // instance.rs:125-134
+SHIM_HD Ray object_ray(const DevObject& ob, const Ray& w) {
+    Ray r = w;
+    if (ob.flags & OBJ_TRANSLATE) r.o = r.o - mk3(ob.dx, ob.dy, ob.dz);
+    if (ob.flags & OBJ_ROTATE) { r.o = rot_y(r.o, ob.sin_t, ob.cos_t); r.d = rot_y(r.d, ob.sin_t, ob.cos_t); }
+    return r;
+}
+SHIM_HD void make_ctx(RayCtx& c, const Ray& r) {
+    c.r = r;
+    c.inv_d = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    c.ox = (double)r.o.x; c.oy = (double)r.o.y; c.oz = (double)r.o.z;
+    c.dx = (double)r.d.x; c.dy = (double)r.d.y; c.dz = (double)r.d.z;
+    c.a = (c.dx * c.dx) + (c.dy * c.dy) + (c.dz * c.dz);
+}
+
+struct TraceCounters { uint32_t nodes, prims; };
+
+// ---------------------------------------------------------------------------- primitives
+// geometry/sphere.rs:50-89 (f64 quadratic; accepts root == t_max)
+SHIM_HD bool hit_sphere(const double* s, const RayCtx& c, float t_min, float t_max, float& t_out) {
+    double ocx = c.ox - s[0], ocy = c.oy - s[1], ocz = c.oz - s[2];
+    double half_b = (ocx * c.dx) + (ocy * c.dy) + (ocz * c.dz);
+    double cc = ((ocx * ocx) + (ocy * ocy) + (ocz * ocz)) - s[3];
+    double disc = half_b * half_b - c.a * cc;
+#if defined(__CUDA_ARCH__)
+    if (__double2hiint(disc) < 0) return false;
+#else
+    if (signbit(disc)) return false;
+#endif
+    double sq = sqrt(disc);
+    double root = (-half_b - sq) / c.a;
+    if (root < (double)t_min || (double)t_max < root) {
+        root = (-half_b + sq) / c.a;
+        if (root < (double)t_min || (double)t_max < root) return false;
+    }
+    t_out = (float)root;
+    return true;
+}
+// geometry/moving_sphere.rs:47-75 (all f32)
+SHIM_HD f3 msphere_center(const f4* m, float time) {
+    f3 c0 = xyz(m[0]), c1 = xyz(m[1]);
+    float time0 = m[1].w, time1 = m[2].x;
+    return c0 + ((time - time0) / (time1 - time0)) * (c1 - c0);
+}
+SHIM_HD bool hit_msphere(const f4* m, const Ray& r, float t_min, float t_max, float& t_out) {
+    float radius = m[0].w;
+    f3 oc = r.o - msphere_center(m, r.time);
+    float a = dot3(r.d, r.d);
+    float half_b = dot3(oc, r.d);
+    float c = dot3(oc, oc) - radius * radius;
+    float disc = half_b * half_b - a * c;
+    if (signbit_f(disc)) return false;
+    float sq = sqrtf(disc);
+    float root = (-half_b - sq) / a;
+    if (root < t_min || t_max < root) {
+        root = (-half_b + sq) / a;
+        if (root < t_min || t_max < root) return false;
+    }
+    t_out = root;
+    return true;
+}
+// geometry/rectangle.rs:37-65 / 99-127 / 161-189.  axis: 2 = Xy (a=x,b=y), 1 = Xz (a=x,b=z), 0 = Yz (a=y,b=z)
+SHIM_HD bool hit_rect_raw(int axis, float a0, float a1, float b0, float b1, float k, const Ray& r, float t_min, float t_max,
+                          float& t_out) {
+    int ia = axis == 0 ? 1 : 0, ib = axis == 2 ? 1 : 2;
+    float t = (k - comp(r.o, axis)) / comp(r.d, axis);
+    if (t < t_min || t > t_max) return false;
+    float a = comp(r.o, ia) + t * comp(r.d, ia);
+    float b = comp(r.o, ib) + t * comp(r.d, ib);
+    if (a < a0 || a > a1 || b < b0 || b > b1) return false;
+    t_out = t;
+    return true;
+}
+SHIM_HD bool hit_rect(const f4* q, const Ray& r, float t_min, float t_max, float& t_out) {
+    return hit_rect_raw(f2i(q[1].y), q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, r, t_min, t_max, t_out);
+}
+// geometry/triangle.rs:32-92 (Moller-Trumbore, two-sided); q = {p0, e1, e2}
+SHIM_HD bool hit_tri(const f4* q, const Ray& r, float t_min, float t_max, float& t_out) {
+    const float epsilon = 0.0000001f;
+    f3 p0 = xyz(q[0]), e1 = xyz(q[1]), e2 = xyz(q[2]);
+    f3 h = cross3(r.d, e2);
+    float a = dot3(e1, h);
+    if (a > -epsilon && a < epsilon) return false;
+    float f = 1.0f / a;
+    f3 s = r.o - p0;
+    float u = f * dot3(s, h);
+    if (u < 0.0f || u > 1.0f) return false;
+    f3 qq = cross3(s, e1);
+    float v = f * dot3(r.d, qq);
+    if (v < 0.0f || u + v > 1.0f) return false;
+    float t = f * dot3(e2, qq);
+    if (t < t_min || t > t_max) return false;
+    if (t > epsilon) { t_out = t; return true; }
+    return false;
+}
+// geometry/cube.rs:23-93: list of six rects (z-min, z-max, y-min, y-max, x-min, x-max), later wins ties
+SHIM_HD void cube_side(const f4* q, int face, int& axis, float& a0, float& a1, float& b0, float& b1, float& k) {
+    f3 mn = xyz(q[0]), mx = xyz(q[1]);
+    if (face < 2) { axis = 2; a0 = mn.x; a1 = mx.x; b0 = mn.y; b1 = mx.y; k = face == 0 ? mn.z : mx.z; }
+    else if (face < 4) { axis = 1; a0 = mn.x; a1 = mx.x; b0 = mn.z; b1 = mx.z; k = face == 2 ? mn.y : mx.y; }
+    else { axis = 0; a0 = mn.y; a1 = mx.y; b0 = mn.z; b1 = mx.z; k = face == 4 ? mn.x : mx.x; }
+}
+SHIM_HD bool hit_cube(const f4* q, const Ray& r, float t_min, float t_max, float& t_out, int& face_out) {
+    float closest = t_max;
+    bool any = false;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        int axis; float a0, a1, b0, b1, k, t;
+        cube_side(q, f, axis, a0, a1, b0, b1, k);
+        if (hit_rect_raw(axis, a0, a1, b0, b1, k, r, t_min, closest, t)) { closest = t; face_out = f; any = true; }
+    }
+    t_out = closest;
+    return any;
+}
+
+SHIM_HD bool hit_prim(const SceneView& sv, uint32_t ref, const RayCtx& c, float t_min, float t_max, float& t, int& face) {
+    uint32_t i = prim_index(ref);
+    switch (prim_type(ref)) {
+    case PT_SPHERE: return hit_sphere(sv.sph + 4 * (size_t)i, c, t_min, t_max, t);
+    case PT_MSPHERE: return hit_msphere(sv.msph + 3 * (size_t)i, c.r, t_min, t_max, t);
+    case PT_RECT: return hit_rect(sv.rect + 2 * (size_t)i, c.r, t_min, t_max, t);
+    case PT_TRI: return hit_tri(sv.tri + 3 * (size_t)i, c.r, t_min, t_max, t);
+    case PT_CUBE: return hit_cube(sv.cube + 2 * (size_t)i, c.r, t_min, t_max, t, face);
+    default: return false;
+    }
+}
+
+// ---------------------------------------------------------------------------- BVH traversal
+// Result contract (bvh.rs:363-417): the brute-force closest hit over the subtree's
+// primitives, each tested as Hittable::hit(ray, t_min, t_max); among primitives with exactly
+// equal t the one latest in left-to-right leaf order wins (`left.t < right.t` else right).
+// Any visiting order satisfies it as long as ties are resolved by leaf rank.
+SHIM_HD bool slab(f3 mn, f3 mx, const RayCtx& c, float t_min, float t_max, float& t_near) {
+    float x0 = (mn.x - c.r.o.x) * c.inv_d.x, x1 = (mx.x - c.r.o.x) * c.inv_d.x;
+    float y0 = (mn.y - c.r.o.y) * c.inv_d.y, y1 = (mx.y - c.r.o.y) * c.inv_d.y;
+    float z0 = (mn.z - c.r.o.z) * c.inv_d.z, z1 = (mx.z - c.r.o.z) * c.inv_d.z;
+    // fminf/fmaxf drop NaNs (0 * inf), which only makes the test more permissive
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_min));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+    t_near = tn;
+    return !(tf < tn);  // aabb.rs:36 rejects only when t_max < t_min
+}
+
+struct BvhBest { float t; int rank; uint32_t prim; int face; int leaf; };
+
+SHIM_HD void bvh_leaf_test(const SceneView& sv, int child, int rank, int node_index, const RayCtx& c, float t_min, BvhBest& best,
+                           TraceCounters* cnt) {
+    uint32_t ref = ~(uint32_t)child;
+    float t; int face = 0;
+    if (cnt) cnt->prims++;
+    if (hit_prim(sv, ref, c, t_min, best.t, t, face)) {
+        if (t < best.t || rank > best.rank) { best.t = t; best.rank = rank; best.prim = ref; best.face = face; best.leaf = node_index; }
+    }
+}
+
+#define SHIM_BVH_STACK 40
+SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, float t_min, float t_max, BvhBest& best,
+                         TraceCounters* cnt) {
+    best.t = t_max; best.rank = -1; best.prim = 0; best.face = 0; best.leaf = -1;
+    int stack[SHIM_BVH_STACK];
+    int sp = 0;
+    int node = start_node;
+    for (;;) {
+        const DevNode& n = sv.nodes[node];
+        f4 na = n.a, nb = n.b, nc = n.c;
+        i4 nd = n.d;
+        if (cnt) cnt->nodes++;
+        float tl, tr;
+        bool hl = nd.x != CHILD_NONE && slab(mk3(na.x, na.y, na.z), mk3(na.w, nb.x, nb.y), c, t_min, best.t, tl);
+        bool hr = nd.y != CHILD_NONE && slab(mk3(nb.z, nb.w, nc.x), mk3(nc.y, nc.z, nc.w), c, t_min, best.t, tr);
+        // primitive children are tested on the spot
+        if (hl && nd.x < 0) { bvh_leaf_test(sv, nd.x, nd.w, node, c, t_min, best, cnt); hl = false; }
+        if (hr && nd.y < 0) {
+            // the left primitive may have shrunk best.t; re-check the right box cheaply
+            if (!(best.t < tr)) bvh_leaf_test(sv, nd.y, nd.w + (nd.x < 0 ? 1 : 0), node, c, t_min, best, cnt);
+            hr = false;
+        }
+        if (hl && hr) {
+            int nearc = nd.x, farc = nd.y;
+            if (tr < tl) { nearc = nd.y; farc = nd.x; }
+            if (sp < SHIM_BVH_STACK) stack[sp++] = farc;
+            node = nearc;
+        } else if (hl) {
+            node = nd.x;
+        } else if (hr) {
+            node = nd.y;
+        } else {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return best.rank >= 0;
+}
+
+// shape of one top-level object against its object-space ray
+SHIM_HD bool shape_hit(const SceneView& sv, const DevObject& ob, const RayCtx& c, float t_min, float t_max, float& t, uint32_t& prim,
+                       int& face, int& leaf, TraceCounters* cnt) {
+    if (ob.kind == OBJ_PRIM) {
+        face = 0; leaf = -1;
+        if (cnt) cnt->prims++;
+        if (hit_prim(sv, (uint32_t)ob.ref, c, t_min, t_max, t, face)) { prim = (uint32_t)ob.ref; return true; }
+        return false;
+    }
+    BvhBest best;
+    if (bvh_closest(sv, ob.ref, c, t_min, t_max, best, cnt)) { t = best.t; prim = best.prim; face = best.face; leaf = best.leaf; return true; }
+    return false;
+}
+
+// HittableList::hit over the flattened world (hittable.rs:100-118), with ConstantMedium::hit
+// (hittable.rs:177-233) for medium objects.  `rng` must be keyed to STAGE_INTERSECT.
+SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float t_max, Rng& rng, TraceCounters* cnt) {
+    Hit h; h.t = t_max; h.obj = -1; h.prim = 0; h.face = 0;
+    float closest = t_max;
+    for (int oi = 0; oi < sv.n_objects; ++oi) {
+        const DevObject& ob = sv.objects[oi];
+        RayCtx c;
+        make_ctx(c, object_ray(ob, ray));
+        float t; uint32_t prim; int face, leaf;
+        if (ob.flags & OBJ_MEDIUM) {
+            float t1, t2;
+            if (!shape_hit(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, leaf, cnt)) continue;
+            if (!shape_hit(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, leaf, cnt)) continue;
+            if (t1 < t_min) t1 = t_min;
+            if (t2 > closest) t2 = closest;
+            if (t1 >= t2) continue;
+            if (t1 < 0.0f) t1 = 0.0f;
+            float ray_length = len3(ray.d);
+            float dist_inside = (t2 - t1) * ray_length;
+            float hit_distance = ob.neg_inv_density * logf(rng_uniform01(rng));
+            if (hit_distance > dist_inside) continue;
+            t = t1 + hit_distance / ray_length;
+            closest = t;
+            h.t = t; h.obj = oi; h.prim = 0; h.face = 0;
+        } else if (shape_hit(sv, ob, c, t_min, closest, t, prim, face, leaf, cnt)) {
+            closest = t;
+            h.t = t; h.obj = oi; h.prim = prim; h.face = face;
+        }
+    }
+    return h;
+}
+
+SHIM_HD int prim_material(const SceneView& sv, uint32_t ref) {
+    uint32_t i = prim_index(ref);
+    switch (prim_type(ref)) {
+    case PT_SPHERE: return sv.sph_mat[i];
+    case PT_MSPHERE: return f2i(sv.msph[3 * (size_t)i + 2].y);
+    case PT_RECT: return f2i(sv.rect[2 * (size_t)i + 1].z);
+    case PT_TRI: return f2i(sv.tri[3 * (size_t)i].w);
+    default: return f2i(sv.cube[2 * (size_t)i].w);
+    }
+}
+SHIM_HD int hit_material(const SceneView& sv, const Hit& h) {
+    const DevObject& ob = sv.objects[h.obj];
+    return (ob.flags & OBJ_MEDIUM) ? ob.phase_mat : prim_material(sv, h.prim);
+}
+SHIM_HD int hit_handle(const SceneView& sv, const Hit& h) {
+    if (h.obj < 0) return -1;
+    const DevObject& ob = sv.objects[h.obj];
+    if (ob.flags & OBJ_MEDIUM) return ob.handle;
+    return sv.handle[prim_type(h.prim)][prim_index(h.prim)];
+}
+
+// ---------------------------------------------------------------------------- hit record
+struct HitRec { f3 point, normal; float t, u, v; bool front_face; int material; };
+
+// geometry/sphere.rs:41-46
+SHIM_HD void sphere_uv(f3 p, float& u, float& v) {
+    float theta = acosf(-p.y);
+    float phi = atan2f(-p.z, p.x) + SHIM_PI;
+    u = phi / (2.0f * SHIM_PI);
+    v = theta / SHIM_PI;
+}
+// HitRecord::new, hittable.rs:28-52
+SHIM_HD void rec_new(HitRec& rec, const Ray& r, f3 outward, float t, float u, float v, int material) {
+    rec.point = ray_at(r, t);
+    rec.front_face = signbit_f(dot3(r.d, outward));
+    rec.normal = rec.front_face ? outward : -outward;
+    rec.t = t; rec.u = u; rec.v = v; rec.material = material;
+}
+// Rebuilds the HitRecord the reference's hit() chain would have returned for this hit.
+// `need_uv`: the sphere uv (acos/atan2) is only evaluated when the material's texture reads it.
+SHIM_HD void reconstruct_hit(const SceneView& sv, const Ray& ray, const Hit& h, bool need_uv, HitRec& rec) {
+    const DevObject& ob = sv.objects[h.obj];
+    if (ob.flags & OBJ_MEDIUM) {  // hittable.rs:216-231
+        rec.point = ray_at(ray, h.t);
+        rec.normal = mk3(1.0f, 0.0f, 0.0f);
+        rec.t = h.t; rec.u = 0.0f; rec.v = 0.0f; rec.front_face = true; rec.material = ob.phase_mat;
+        return;
+    }
+    Ray r = object_ray(ob, ray);
+    uint32_t i = prim_index(h.prim);
+    switch (prim_type(h.prim)) {
+    case PT_SPHERE: {
+        f4 s = sv.sph_s[i];
+        f3 point = ray_at(r, h.t);
+        f3 n = (point - xyz(s)) / s.w;
+        float u = 0.0f, v = 0.0f;
+        if (need_uv) sphere_uv(n, u, v);
+        rec_new(rec, r, n, h.t, u, v, sv.sph_mat[i]);
+        break;
+    }
+    case PT_MSPHERE: {
+        const f4* m = sv.msph + 3 * (size_t)i;
+        f3 point = ray_at(r, h.t);
+        f3 n = (point - msphere_center(m, r.time)) / m[0].w;
+        float u = 0.0f, v = 0.0f;
+        if (need_uv) sphere_uv(n, u, v);
+        rec_new(rec, r, n, h.t, u, v, f2i(m[2].y));
+        break;
+    }
+    case PT_TRI: {
+        const f4* q = sv.tri + 3 * (size_t)i;
+        f3 n = normalize3(cross3(xyz(q[1]), xyz(q[2])));
+        rec_new(rec, r, n, h.t, 0.0f, 0.0f, f2i(q[0].w));
+        break;
+    }
+    default: {  // PT_RECT, PT_CUBE
+        int axis, mat; float a0, a1, b0, b1, k;
+        if (prim_type(h.prim) == PT_RECT) {
+            const f4* q = sv.rect + 2 * (size_t)i;
+            axis = f2i(q[1].y); a0 = q[0].x; a1 = q[0].y; b0 = q[0].z; b1 = q[0].w; k = q[1].x; mat = f2i(q[1].z);
+        } else {
+            const f4* q = sv.cube + 2 * (size_t)i;
+            cube_side(q, h.face, axis, a0, a1, b0, b1, k);
+            mat = f2i(q[0].w);
+        }
+        int ia = axis == 0 ? 1 : 0, ib = axis == 2 ? 1 : 2;
+        float a = comp(r.o, ia) + h.t * comp(r.d, ia);
+        float b = comp(r.o, ib) + h.t * comp(r.d, ib);
+        float u = (a - a0) / (a1 - a0);
+        float v = (b - b0) / (b1 - b0);
+        f3 n = axis == 0 ? mk3(1, 0, 0) : (axis == 1 ? mk3(0, 1, 0) : mk3(0, 0, 1));
+        rec_new(rec, r, n, h.t, u, v, mat);
+        break;
+    }
+    }
+    if (ob.flags & OBJ_ROTATE) {  // instance.rs:124-141
+        f3 p = rot_y_back(rec.point, ob.sin_t, ob.cos_t);
+        f3 n = rot_y_back(rec.normal, ob.sin_t, ob.cos_t);
+        rec.point = p;
+        bool front = dot3(r.d, n) < 0.0f;  // set_face_normal with the rotated ray; front_face is left untouched
+        rec.normal = front ? n : -n;
+    }
+    if (ob.flags & OBJ_TRANSLATE) rec.point = rec.point + mk3(ob.dx, ob.dy, ob.dz);  // instance.rs:40-42
+}
+
+// ---------------------------------------------------------------------------- textures
+// Perlin / Turbulence standing in for the `noise` crate; f64 like the crate.
+SHIM_HD double perlin_fade(double t) { return t * t * t * (t * (t * 6.0 - 15.0) + 10.0); }
+SHIM_HD double perlin_lerp(double t, double a, double b) { return a + t * (b - a); }
+SHIM_HD double perlin_grad(int h, double x, double y, double z) {
+    h &= 15;
+    double u = h < 8 ? x : y;
+    double v = h < 4 ? y : ((h == 12 || h == 14) ? x : z);
+    return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+}
+SHIM_HD double perlin_get(const uint8_t* perm, double x, double y, double z) {
+    double fx = floor(x), fy = floor(y), fz = floor(z);
+    int X = (int)((long long)fx & 255), Y = (int)((long long)fy & 255), Z = (int)((long long)fz & 255);
+    x -= fx; y -= fy; z -= fz;
+    double u = perlin_fade(x), v = perlin_fade(y), w = perlin_fade(z);
+#define SHIM_P(i) ((int)perm[(i) & 255])
+    int A = SHIM_P(X) + Y, AA = SHIM_P(A) + Z, AB = SHIM_P(A + 1) + Z;
+    int B = SHIM_P(X + 1) + Y, BA = SHIM_P(B) + Z, BB = SHIM_P(B + 1) + Z;
+    double r = perlin_lerp(
+        w,
+        perlin_lerp(v, perlin_lerp(u, perlin_grad(SHIM_P(AA), x, y, z), perlin_grad(SHIM_P(BA), x - 1, y, z)),
+                    perlin_lerp(u, perlin_grad(SHIM_P(AB), x, y - 1, z), perlin_grad(SHIM_P(BB), x - 1, y - 1, z))),
+        perlin_lerp(v, perlin_lerp(u, perlin_grad(SHIM_P(AA + 1), x, y, z - 1), perlin_grad(SHIM_P(BA + 1), x - 1, y, z - 1)),
+                    perlin_lerp(u, perlin_grad(SHIM_P(AB + 1), x, y - 1, z - 1), perlin_grad(SHIM_P(BB + 1), x - 1, y - 1, z - 1))));
+#undef SHIM_P
+    return r;
+}
+#define SHIM_FBM_OCTAVES 6
+SHIM_HD double fbm_get(const uint8_t* tables, double x, double y, double z) {
+    const double lac = 2.0943951023931953, pers = 0.5;
+    double result = 0.0, att = pers, denom = 0.0;
+    for (int i = 0; i < SHIM_FBM_OCTAVES; ++i) {
+        double s = perlin_get(tables + 256 * i, x, y, z) * att;
+        denom += att;
+        att *= pers;
+        result += s;
+        x *= lac; y *= lac; z *= lac;
+    }
+    return result * (1.0 / denom);
+}
+// tables: [0] source, [1..6] x-distort octaves, [7..12] y, [13..18] z
+SHIM_HD double turbulence_get(const uint8_t* t, double x, double y, double z) {
+    double x0 = x + 12414.0 / 65536.0, y0 = y + 65124.0 / 65536.0, z0 = z + 31337.0 / 65536.0;
+    double x1 = x + 26519.0 / 65536.0, y1 = y + 18128.0 / 65536.0, z1 = z + 60493.0 / 65536.0;
+    double x2 = x + 53820.0 / 65536.0, y2 = y + 11213.0 / 65536.0, z2 = z + 44845.0 / 65536.0;
+    double xd = x + fbm_get(t + 256 * 1, x0, y0, z0) * 1.0;
+    double yd = y + fbm_get(t + 256 * 7, x1, y1, z1) * 1.0;
+    double zd = z + fbm_get(t + 256 * 13, x2, y2, z2) * 1.0;
+    return perlin_get(t, xd, yd, zd);
+}
+
+// texture record: a = {kind, even|w, odd|h, blob offset}, b = {r, g, b, scale}
+SHIM_HD f3 tex_value(const SceneView& sv, int ti, float u, float v, f3 p) {
+    for (int guard = 0; guard < 16; ++guard) {
+        f4 a = sv.textures[2 * (size_t)ti], b = sv.textures[2 * (size_t)ti + 1];
+        int kind = f2i(a.x);
+        if (kind == TEX_SOLID) return mk3(b.x, b.y, b.z);
+        if (kind == TEX_CHECKER) {  // checker.rs:27-37
+            float sines = sinf(b.w * p.x) * sinf(b.w * p.y) * sinf(b.w * p.z);
+            ti = signbit_f(sines) ? f2i(a.z) : f2i(a.y);
+            continue;
+        }
+        if (kind == TEX_MARBLE) {   // marble.rs:23-29
+            float n = (float)turbulence_get(sv.perlin + (size_t)(uint32_t)f2i(a.w), (double)p.x, (double)p.y, (double)p.z);
+            float g = 0.5f * (1.0f + sinf(b.w * p.z + 10.0f * n));
+            return mk3(1.0f * g, 1.0f * g, 1.0f * g);
+        }
+        {                           // image_texture.rs:21-52
+            uint32_t w = (uint32_t)f2i(a.y), hgt = (uint32_t)f2i(a.z);
+            float uu = fminf(fmaxf(u, 0.0f), 1.0f);
+            float vv = fminf(fmaxf(v, 0.0f), 1.0f);
+            vv = 1.0f - vv;
+            uint32_t i = (uint32_t)(uu * (float)w), j = (uint32_t)(vv * (float)hgt);
+            if (i >= w) i = w - 1;
+            if (j >= hgt) j = hgt - 1;
+            const uint8_t* px = sv.images + (size_t)(uint32_t)f2i(a.w) + ((size_t)j * w + i) * 3;
+            const float s = 1.0f / 255.0f;
+            return mk3((float)px[0] * s, (float)px[1] * s, (float)px[2] * s);
+        }
+    }
+    return mk3(0, 0, 0);
+}
+// does evaluating this texture read (u, v)?  (only image textures do)
+SHIM_HD bool tex_needs_uv(const SceneView& sv, int ti) {
+    // checker children may be images; walk both branches iteratively with a tiny stack
+    int stack[8]; int sp = 0; stack[sp++] = ti;
+    while (sp > 0) {
+        int t = stack[--sp];
+        f4 a = sv.textures[2 * (size_t)t];
+        int kind = f2i(a.x);
+        if (kind == TEX_IMAGE) return true;
+        if (kind == TEX_CHECKER && sp + 2 <= 8) { stack[sp++] = f2i(a.y); stack[sp++] = f2i(a.z); }
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------- materials
+// material record: a = {kind, tex, fuzz, ior}, b = {albedo rgb, needs_uv}
+SHIM_HD f3 reflect3(f3 v, f3 n) { return v - 2.0f * dot3(v, n) * n; }  // materials/utils.rs:37-39
+SHIM_HD f3 refract3(f3 uv, f3 n, float eta) {                          // materials/utils.rs:41-46
+    float cos_theta = fminf(dot3(-uv, n), 1.0f);
+    f3 perp = eta * (uv + cos_theta * n);
+    f3 par = -sqrtf(fabsf(1.0f - dot3(perp, perp))) * n;
+    return par + perp;
+}
+SHIM_HD float schlick(float cosine, float ref_idx) {                   // dialectric.rs:26-29
+    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    r0 = r0 * r0;
+    float x = 1.0f - cosine;
+    float x2 = x * x;
+    return r0 + (1.0f - r0) * (x * (x2 * x2));
+}
+SHIM_HD f3 mat_emit(const SceneView& sv, int mi, const HitRec& rec) {  // material.rs:20-22, diffuse_light.rs:34-36
+    f4 a = sv.materials[2 * (size_t)mi];
+    if (f2i(a.x) == MAT_DIFFUSE_LIGHT) return tex_value(sv, f2i(a.y), rec.u, rec.v, rec.point);
+    return mk3(0, 0, 0);
+}
+// `rng` must be keyed to STAGE_SCATTER
+// `kind` is the material's kind (a compile-time constant in the material-sorted shade kernels)
+SHIM_HD bool mat_scatter(const SceneView& sv, int kind, int mi, const Ray& ray, const HitRec& rec, Rng& rng, f3& att, Ray& out) {
+    f4 a = sv.materials[2 * (size_t)mi], b = sv.materials[2 * (size_t)mi + 1];
+    switch (kind) {
+    case MAT_LAMBERTIAN: {  // lambertian.rs:35-52
+        f3 dir = rec.normal + normalize3(random_in_unit_sphere(rng));
+        if (fabsf(dir.x) < SHIM_F32_EPS && fabsf(dir.y) < SHIM_F32_EPS && fabsf(dir.z) < SHIM_F32_EPS) dir = rec.normal;
+        out.o = rec.point; out.d = dir; out.time = ray.time;
+        att = tex_value(sv, f2i(a.y), rec.u, rec.v, rec.point);
+        return true;
+    }
+    case MAT_METAL: {       // metal.rs:26-42
+        f3 reflected = reflect3(normalize3(ray.d), rec.normal);
+        out.o = rec.point; out.d = reflected + a.z * random_in_unit_sphere(rng); out.time = ray.time;
+        att = mk3(b.x, b.y, b.z);
+        return dot3(out.d, rec.normal) > 0.0f;
+    }
+    case MAT_DIELECTRIC: {  // dialectric.rs:33-60
+        att = mk3(1, 1, 1);
+        float ratio = rec.front_face ? 1.0f / a.w : a.w;
+        f3 unit = normalize3(ray.d);
+        float cos_theta = fminf(dot3(-unit, rec.normal), 1.0f);
+        float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        bool cannot = ratio * sin_theta > 1.0f;
+        f3 dir;
+        if (cannot || schlick(cos_theta, ratio) > rng_uniform01(rng)) dir = reflect3(unit, rec.normal);
+        else dir = refract3(unit, rec.normal, ratio);
+        out.o = rec.point; out.d = dir; out.time = ray.time;
+        return true;
+    }
+    case MAT_DIFFUSE_LIGHT: return false;  // diffuse_light.rs:25-32
+    default: {              // isotropic.rs:32-42
+        out.o = rec.point; out.d = random_in_unit_sphere(rng); out.time = ray.time;
+        att = tex_value(sv, f2i(a.y), rec.u, rec.v, rec.point);
+        return true;
+    }
+    }
+}
+SHIM_HD int mat_kind(const SceneView& sv, int mi) { return f2i(sv.materials[2 * (size_t)mi].x); }
+SHIM_HD bool mat_needs_uv(const SceneView& sv, int mi) { return sv.materials[2 * (size_t)mi + 1].w != 0.0f; }
+
+// ---------------------------------------------------------------------------- hrpp.rs:132-193
+SHIM_HD uint32_t hrpp_map_float(float v) {
+    uint32_t bits = (uint32_t)f2i(v);
+    uint32_t sign = (bits >> 31) & 1u, expo = (bits >> 25) & 0x3fu, mant = (bits >> 17) & 0x3fu;
+    return (sign << 15) | (expo << 7) | mant;
+}
+SHIM_HD uint64_t hrpp_hash(const Ray& r) {
+    uint64_t h0 = hrpp_map_float(r.o.x) ^ hrpp_map_float(r.d.z);
+    uint64_t h1 = hrpp_map_float(r.o.y) ^ hrpp_map_float(r.d.y);
+    uint64_t h2 = hrpp_map_float(r.o.z) ^ hrpp_map_float(r.d.x);
+    return h0 | (h1 << 16) | (h2 << 32);
+}
+
+}  // namespace shim

@@ -1,0 +1,461 @@
+// shim_scene.cpp — host builder, bvh.rs-style tree build and the flattener.
+#include "shim_scene.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+
+namespace shim {
+
+static const float kEps = 1.1920929e-07f;  // f32::EPSILON
+static const float kPi = 3.14159265358979323846f;
+
+static Box box_union(const Box& a, const Box& b) {  // Aabb::union, aabb.rs:43-62
+    Box r;
+    for (int i = 0; i < 3; ++i) { r.mn[i] = std::fmin(a.mn[i], b.mn[i]); r.mx[i] = std::fmax(a.mx[i], b.mx[i]); }
+    return r;
+}
+
+bool SceneBuilder::bounding_box(int hid, float t0, float t1, Box& out) const {
+    const HostHittable& h = hittables[hid];
+    const float* p = h.p;
+    switch (h.kind) {
+    case H_SPHERE:  // sphere.rs:105-109
+        for (int i = 0; i < 3; ++i) { out.mn[i] = p[i] - p[3]; out.mx[i] = p[i] + p[3]; }
+        return true;
+    case H_MSPHERE: {  // moving_sphere.rs:86-93; the true union of the start and end boxes
+        // (the reference's end box reuses center(time_0) for its min, which equals this box
+        // whenever the motion is non-negative on every axis, as in all of its scenes)
+        Box a, b;
+        for (int i = 0; i < 3; ++i) {
+            float ca = p[i] + ((t0 - p[6]) / (p[7] - p[6])) * (p[3 + i] - p[i]);
+            float cb = p[i] + ((t1 - p[6]) / (p[7] - p[6])) * (p[3 + i] - p[i]);
+            a.mn[i] = ca - p[8]; a.mx[i] = ca + p[8];
+            b.mn[i] = cb - p[8]; b.mx[i] = cb + p[8];
+        }
+        out = box_union(a, b);
+        return true;
+    }
+    case H_RECT: {  // rectangle.rs:67-73 / 129-135 / 191-197
+        int ia = h.axis == 0 ? 1 : 0, ib = h.axis == 2 ? 1 : 2;
+        out.mn[ia] = p[0]; out.mx[ia] = p[1];
+        out.mn[ib] = p[2]; out.mx[ib] = p[3];
+        out.mn[h.axis] = p[4] - kEps; out.mx[h.axis] = p[4] + kEps;
+        return true;
+    }
+    case H_TRI:  // triangle.rs:94-107
+        for (int i = 0; i < 3; ++i) {
+            out.mn[i] = std::fmin(p[i], std::fmin(p[3 + i], p[6 + i])) - kEps;
+            out.mx[i] = std::fmax(p[i], std::fmax(p[3 + i], p[6 + i])) + kEps;
+        }
+        return true;
+    case H_CUBE:  // cube.rs:95-97
+        for (int i = 0; i < 3; ++i) { out.mn[i] = p[i]; out.mx[i] = p[3 + i]; }
+        return true;
+    default:
+        return false;
+    }
+}
+
+static int total_cmp(float a, float b) {  // f32::total_cmp
+    int32_t l, r;
+    memcpy(&l, &a, 4); memcpy(&r, &b, 4);
+    l ^= (int32_t)(((uint32_t)(l >> 31)) >> 1);
+    r ^= (int32_t)(((uint32_t)(r >> 31)) >> 1);
+    return l < r ? -1 : (l > r ? 1 : 0);
+}
+static uint64_t splitmix64(uint64_t& s) {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static int bvh_height(const std::vector<HostBvhNode>& nodes, int i) {  // BvhNode::max_depth, bvh.rs:335-350
+    int l = nodes[i].left >= 0 ? bvh_height(nodes, nodes[i].left) : 0;
+    int r = nodes[i].right >= 0 ? bvh_height(nodes, nodes[i].right) : 0;
+    return (l > r ? l : r) + 1;
+}
+
+int SceneBuilder::build_bvh(int list, float t0, float t1, uint64_t axis_seed, bool predictor) {
+    if (!ok_hit(list) || hittables[list].kind != H_LIST) { err = "shim_bvh: not a list"; return SHIM_ERR_INVALID_; }
+    std::vector<int> objs = hittables[list].items;
+    if (objs.empty()) { err = "shim_bvh: empty list"; return SHIM_ERR_INVALID_; }
+    // cache the comparator boxes (bounding_box(0,0), bvh.rs:420-428) and the node boxes (t0,t1)
+    std::unordered_map<int, Box> cmp_box, node_box;
+    for (int o : objs) {
+        Box a, b;
+        if (!bounding_box(o, 0.0f, 0.0f, a) || !bounding_box(o, t0, t1, b)) {
+            err = "shim_bvh: a BVH may only contain spheres, moving spheres, rects, triangles and cubes";
+            return SHIM_ERR_UNSUPPORTED_;
+        }
+        cmp_box[o] = a; node_box[o] = b;
+    }
+    HostHittable bvh;
+    bvh.kind = H_BVH; bvh.child = list; bvh.t0 = t0; bvh.t1 = t1; bvh.predictor = predictor;
+    bvh.nodes.reserve(objs.size() * 2 + 1);
+    uint64_t state = axis_seed;
+    std::function<int(int*, size_t)> rec = [&](int* o, size_t n) -> int {
+        int axis = (int)(splitmix64(state) % 3ull);  // stands in for rng.gen_range(0..=2), bvh.rs:255-257
+        auto less = [&](int a, int b) { return total_cmp(cmp_box[a].mn[axis], cmp_box[b].mn[axis]) < 0; };
+        HostBvhNode node;
+        node.parent = -1;
+        if (n == 1) { node.left = ~o[0]; node.right = ~o[0]; }
+        else if (n == 2) {
+            if (less(o[0], o[1])) { node.left = ~o[0]; node.right = ~o[1]; }
+            else { node.left = ~o[1]; node.right = ~o[0]; }
+        } else {
+            std::stable_sort(o, o + n, less);
+            size_t mid = n / 2;
+            node.left = rec(o, mid);
+            node.right = rec(o + mid, n - mid);
+        }
+        Box lb = node.left >= 0 ? bvh.nodes[node.left].box : node_box[~node.left];
+        Box rb = node.right >= 0 ? bvh.nodes[node.right].box : node_box[~node.right];
+        node.box = box_union(lb, rb);
+        int idx = (int)bvh.nodes.size();
+        if (node.left >= 0) bvh.nodes[node.left].parent = idx;
+        if (node.right >= 0) bvh.nodes[node.right].parent = idx;
+        bvh.nodes.push_back(node);
+        return idx;
+    };
+    bvh.root = rec(objs.data(), objs.size());
+    bvh.height = bvh_height(bvh.nodes, bvh.root);
+    return add_hittable(bvh);
+}
+
+int SceneBuilder::bvh_from_nodes(int n, const int32_t* left, const int32_t* right, int root, float t0, float t1, bool predictor) {
+    if (n <= 0 || root < 0 || root >= n || !left || !right) { err = "shim_bvh_from_nodes: bad arguments"; return SHIM_ERR_INVALID_; }
+    HostHittable bvh;
+    bvh.kind = H_BVH; bvh.t0 = t0; bvh.t1 = t1; bvh.predictor = predictor; bvh.root = root;
+    bvh.nodes.resize(n);
+    std::vector<int> state(n, 0);
+    for (int i = 0; i < n; ++i) { bvh.nodes[i].left = left[i]; bvh.nodes[i].right = right[i]; bvh.nodes[i].parent = -1; }
+    // boxes bottom-up (iterative post-order); also validates that the graph is a tree
+    std::vector<int> stack{root};
+    while (!stack.empty()) {
+        int i = stack.back();
+        HostBvhNode& nd = bvh.nodes[i];
+        if (state[i] == 0) {
+            state[i] = 1;
+            for (int c : {nd.left, nd.right}) {
+                if (c >= 0) {
+                    if (c >= n || state[c] != 0) { err = "shim_bvh_from_nodes: not a tree"; return SHIM_ERR_INVALID_; }
+                    bvh.nodes[c].parent = i;
+                    stack.push_back(c);
+                } else if (!ok_hit(~c)) { err = "shim_bvh_from_nodes: bad primitive id"; return SHIM_ERR_INVALID_; }
+            }
+        } else {
+            stack.pop_back();
+            Box b[2];
+            int k = 0;
+            for (int c : {nd.left, nd.right}) {
+                if (c >= 0) b[k] = bvh.nodes[c].box;
+                else if (!bounding_box(~c, t0, t1, b[k])) { err = "shim_bvh_from_nodes: unsupported BVH member"; return SHIM_ERR_UNSUPPORTED_; }
+                ++k;
+            }
+            nd.box = box_union(b[0], b[1]);
+            state[i] = 2;
+        }
+    }
+    bvh.height = bvh_height(bvh.nodes, root);
+    return add_hittable(bvh);
+}
+
+// ---------------------------------------------------------------------------- Perlin tables
+static void perlin_table(uint32_t seed, uint8_t* perm) {
+    for (int i = 0; i < 256; ++i) perm[i] = (uint8_t)i;
+    uint64_t s = 0x5851F42D4C957F2Dull ^ (uint64_t)seed;
+    for (int i = 255; i > 0; --i) {
+        uint32_t j = (uint32_t)(splitmix64(s) % (uint64_t)(i + 1));
+        std::swap(perm[i], perm[j]);
+    }
+}
+void marble_tables(uint32_t seed, std::vector<uint8_t>& out) {
+    size_t base = out.size();
+    out.resize(base + 19 * 256);
+    uint8_t* t = out.data() + base;
+    perlin_table(seed, t);  // Turbulence source = Perlin::new(seed), marble.rs:14-19
+    for (int f = 0; f < 3; ++f)          // x/y/z distortion Fbm seeded 0,1,2
+        for (int o = 0; o < 6; ++o) perlin_table((uint32_t)(f + o), t + 256 * (1 + f * 6 + o));
+}
+
+// ---------------------------------------------------------------------------- flatten
+namespace {
+struct Flattener {
+    SceneBuilder& sb;
+    FlatScene& fs;
+    std::unordered_map<int, uint32_t> prim_of;   // hittable id -> prim_ref
+    std::unordered_map<int, int> bvh_base;       // hittable id -> first node index
+    std::unordered_map<int, int> bvh_pred;       // hittable id -> predictor index
+    int status = 0;
+
+    struct Xf { bool translate = false, rotate = false; float d[3] = {0, 0, 0}; float s = 0, c = 1; int medium = -1; };
+
+    int fail(int code, const std::string& m) { sb.err = m; status = code; return code; }
+
+    uint32_t add_prim(int hid) {
+        auto it = prim_of.find(hid);
+        if (it != prim_of.end()) return it->second;
+        const HostHittable& h = sb.hittables[hid];
+        const float* p = h.p;
+        uint32_t ref = 0;
+        auto bits = [](int i) { float f; memcpy(&f, &i, 4); return f; };
+        switch (h.kind) {
+        case H_SPHERE: {
+            ref = prim_ref(PT_SPHERE, (uint32_t)fs.sph_s.size());
+            double r = (double)p[3];
+            fs.sph.push_back((double)p[0]); fs.sph.push_back((double)p[1]); fs.sph.push_back((double)p[2]); fs.sph.push_back(r * r);
+            fs.sph_s.push_back(f4{p[0], p[1], p[2], p[3]});
+            fs.sph_mat.push_back(h.material);
+            fs.handle[PT_SPHERE].push_back(hid);
+            break;
+        }
+        case H_MSPHERE:
+            ref = prim_ref(PT_MSPHERE, (uint32_t)fs.handle[PT_MSPHERE].size());
+            fs.msph.push_back(f4{p[0], p[1], p[2], p[8]});
+            fs.msph.push_back(f4{p[3], p[4], p[5], p[6]});
+            fs.msph.push_back(f4{p[7], bits(h.material), 0, 0});
+            fs.handle[PT_MSPHERE].push_back(hid);
+            break;
+        case H_RECT:
+            ref = prim_ref(PT_RECT, (uint32_t)fs.handle[PT_RECT].size());
+            fs.rect.push_back(f4{p[0], p[1], p[2], p[3]});
+            fs.rect.push_back(f4{p[4], bits(h.axis), bits(h.material), 0});
+            fs.handle[PT_RECT].push_back(hid);
+            break;
+        case H_TRI:
+            ref = prim_ref(PT_TRI, (uint32_t)fs.handle[PT_TRI].size());
+            fs.tri.push_back(f4{p[0], p[1], p[2], bits(h.material)});
+            fs.tri.push_back(f4{p[3] - p[0], p[4] - p[1], p[5] - p[2], 0});  // edge1 = vertex1 - vertex0, triangle.rs:44
+            fs.tri.push_back(f4{p[6] - p[0], p[7] - p[1], p[8] - p[2], 0});  // edge2
+            fs.handle[PT_TRI].push_back(hid);
+            break;
+        default:  // H_CUBE
+            ref = prim_ref(PT_CUBE, (uint32_t)fs.handle[PT_CUBE].size());
+            fs.cube.push_back(f4{p[0], p[1], p[2], bits(h.material)});
+            fs.cube.push_back(f4{p[3], p[4], p[5], 0});
+            fs.handle[PT_CUBE].push_back(hid);
+            break;
+        }
+        prim_of[hid] = ref;
+        return ref;
+    }
+
+    static bool is_prim(int kind) { return kind == H_SPHERE || kind == H_MSPHERE || kind == H_RECT || kind == H_TRI || kind == H_CUBE; }
+
+    int add_bvh(int hid) {
+        auto it = bvh_base.find(hid);
+        if (it != bvh_base.end()) return it->second;
+        const HostHittable& b = sb.hittables[hid];
+        int base = (int)fs.nodes.size();
+        fs.nodes.resize(base + b.nodes.size());
+        // left-to-right leaf ranks + primitive placement in leaf order (iterative DFS, left first)
+        std::vector<int> rank_base(b.nodes.size(), 0);
+        int rank = 0;
+        // ranks come from a true in-order walk (caller-built trees may mix inner and primitive children)
+        std::function<void(int)> walk = [&](int i) {
+            const HostBvhNode& n = b.nodes[i];
+            bool dup = n.left < 0 && n.right < 0 && n.left == n.right;
+            if (n.left >= 0) walk(n.left);
+            else { rank_base[i] = rank; rank++; }
+            if (n.right >= 0) walk(n.right);
+            else if (!dup) { if (n.left >= 0) rank_base[i] = rank; rank++; }
+        };
+        if (b.height > SHIM_MAX_BVH_HEIGHT) { fail(SHIM_ERR_UNSUPPORTED_, "BVH taller than the traversal stack"); return -1; }
+        walk(b.root);
+        for (size_t i = 0; i < b.nodes.size(); ++i) {
+            const HostBvhNode& n = b.nodes[i];
+            DevNode dn;
+            Box lb{}, rb{};
+            int lref, rref;
+            bool dup = n.left < 0 && n.right < 0 && n.left == n.right;
+            auto child = [&](int c, Box& bx, int& ref) -> bool {
+                if (c >= 0) { bx = b.nodes[c].box; ref = base + c; return true; }
+                int h = ~c;
+                if (!sb.ok_hit(h) || !is_prim(sb.hittables[h].kind)) return false;
+                sb.bounding_box(h, b.t0, b.t1, bx);
+                ref = (int)~add_prim(h);
+                return true;
+            };
+            if (!child(n.left, lb, lref)) { fail(SHIM_ERR_UNSUPPORTED_, "a BVH may only contain primitives and cubes"); return -1; }
+            if (dup) {
+                rref = CHILD_NONE;
+                for (int k = 0; k < 3; ++k) { rb.mn[k] = INFINITY; rb.mx[k] = -INFINITY; }
+            } else if (!child(n.right, rb, rref)) { fail(SHIM_ERR_UNSUPPORTED_, "a BVH may only contain primitives and cubes"); return -1; }
+            dn.a = f4{lb.mn[0], lb.mn[1], lb.mn[2], lb.mx[0]};
+            dn.b = f4{lb.mx[1], lb.mx[2], rb.mn[0], rb.mn[1]};
+            dn.c = f4{rb.mn[2], rb.mx[0], rb.mx[1], rb.mx[2]};
+            // rank of the first primitive child; when only the right child is a primitive the kernel adds 0
+            dn.d = i4{lref, rref, n.parent >= 0 ? base + n.parent : -1, rank_base[i]};
+            fs.nodes[base + i] = dn;
+        }
+        bvh_base[hid] = base;
+        if (b.predictor) { bvh_pred[hid] = (int)fs.predictor_bvh.size(); fs.predictor_bvh.push_back(hid); }
+        return base;
+    }
+
+    void emit(int hid, const Xf& xf) {
+        const HostHittable& h = sb.hittables[hid];
+        DevObject ob;
+        memset(&ob, 0, sizeof ob);
+        ob.predictor = -1;
+        if (h.kind == H_BVH) {
+            int base = add_bvh(hid);
+            if (base < 0) return;
+            ob.kind = OBJ_BVH; ob.ref = base + h.root; ob.n_nodes = (int)h.nodes.size();
+            if (h.predictor) { ob.flags |= OBJ_PREDICTOR; ob.predictor = bvh_pred[hid]; }
+        } else {
+            ob.kind = OBJ_PRIM; ob.ref = (int)add_prim(hid);
+        }
+        if (xf.translate) { ob.flags |= OBJ_TRANSLATE; ob.dx = xf.d[0]; ob.dy = xf.d[1]; ob.dz = xf.d[2]; }
+        if (xf.rotate) { ob.flags |= OBJ_ROTATE; }
+        ob.sin_t = xf.s; ob.cos_t = xf.c;
+        if (xf.medium >= 0) {
+            const HostHittable& m = sb.hittables[xf.medium];
+            ob.flags |= OBJ_MEDIUM; ob.handle = xf.medium; ob.neg_inv_density = m.neg_inv_density; ob.phase_mat = m.phase_mat;
+        }
+        fs.objects.push_back(ob);
+    }
+
+    void visit(int hid, Xf xf, int depth) {
+        if (status) return;
+        if (depth > 64) { fail(SHIM_ERR_UNSUPPORTED_, "hittable nesting too deep (cycle?)"); return; }
+        const HostHittable& h = sb.hittables[hid];
+        switch (h.kind) {
+        case H_LIST:
+            if (xf.medium >= 0) { fail(SHIM_ERR_UNSUPPORTED_, "ConstantMedium over a HittableList boundary is not supported"); return; }
+            for (int it : h.items) visit(it, xf, depth + 1);
+            return;
+        case H_TRANSLATE:
+            if (xf.translate || xf.rotate) { fail(SHIM_ERR_UNSUPPORTED_, "only Translate(RotateY(x)), Translate(x) and RotateY(x) instance chains are supported"); return; }
+            xf.translate = true; xf.d[0] = h.p[0]; xf.d[1] = h.p[1]; xf.d[2] = h.p[2];
+            visit(h.child, xf, depth + 1);
+            return;
+        case H_ROTATE_Y:
+            if (xf.rotate) { fail(SHIM_ERR_UNSUPPORTED_, "only Translate(RotateY(x)), Translate(x) and RotateY(x) instance chains are supported"); return; }
+            xf.rotate = true; xf.s = h.sin_t; xf.c = h.cos_t;
+            visit(h.child, xf, depth + 1);
+            return;
+        case H_MEDIUM:
+            if (xf.translate || xf.rotate || xf.medium >= 0) { fail(SHIM_ERR_UNSUPPORTED_, "a ConstantMedium must not sit under an instance transform or another medium"); return; }
+            xf.medium = hid;
+            visit(h.child, xf, depth + 1);
+            return;
+        default:
+            emit(hid, xf);
+            return;
+        }
+    }
+};
+}  // namespace
+
+int SceneBuilder::flatten(FlatScene& fs) {
+    fs = FlatScene();
+    Flattener f{*this, fs};
+    for (int w : world) f.visit(w, Flattener::Xf(), 0);
+    if (f.status) return f.status;
+    auto bits = [](int i) { float x; memcpy(&x, &i, 4); return x; };
+    // textures
+    for (const HostTexture& t : textures) {
+        f4 a{bits(t.kind), bits(t.even), bits(t.odd), bits(0)}, b{t.color[0], t.color[1], t.color[2], t.scale};
+        if (t.kind == TEX_MARBLE) { a.w = bits((int)fs.perlin.size()); marble_tables(t.seed, fs.perlin); }
+        if (t.kind == TEX_IMAGE) {
+            a.y = bits(t.w); a.z = bits(t.h); a.w = bits((int)fs.images.size());
+            fs.images.insert(fs.images.end(), t.rgb.begin(), t.rgb.end());
+        }
+        fs.textures.push_back(a); fs.textures.push_back(b);
+    }
+    // materials (b.w = 1 when the texture chain reads u,v: only then is the sphere uv evaluated)
+    std::function<bool(int, int)> reads_uv = [&](int t, int depth) -> bool {
+        if (t < 0 || depth > 16) return false;
+        if (textures[t].kind == TEX_IMAGE) return true;
+        if (textures[t].kind == TEX_CHECKER) return reads_uv(textures[t].even, depth + 1) || reads_uv(textures[t].odd, depth + 1);
+        return false;
+    };
+    for (const HostMaterial& m : materials) {
+        fs.materials.push_back(f4{bits(m.kind), bits(m.tex), m.fuzz, m.ior});
+        fs.materials.push_back(f4{m.albedo[0], m.albedo[1], m.albedo[2], reads_uv(m.tex, 0) ? 1.0f : 0.0f});
+    }
+    return 0;
+}
+
+SceneView FlatScene::view() const {
+    SceneView v;
+    memset(&v, 0, sizeof v);
+    v.nodes = nodes.data(); v.sph = sph.data(); v.sph_s = sph_s.data(); v.sph_mat = sph_mat.data();
+    v.msph = msph.data(); v.rect = rect.data(); v.tri = tri.data(); v.cube = cube.data();
+    v.objects = objects.data(); v.materials = materials.data(); v.textures = textures.data();
+    v.images = images.data(); v.perlin = perlin.data();
+    for (int i = 0; i < 5; ++i) v.handle[i] = handle[i].data();
+    v.n_objects = (int)objects.size(); v.n_nodes = (int)nodes.size();
+    return v;
+}
+uint64_t FlatScene::bytes() const {
+    uint64_t b = nodes.size() * sizeof(DevNode) + sph.size() * 8 + sph_s.size() * 16 + sph_mat.size() * 4 +
+                 (msph.size() + rect.size() + tri.size() + cube.size() + materials.size() + textures.size()) * 16 +
+                 objects.size() * sizeof(DevObject) + images.size() + perlin.size();
+    for (int i = 0; i < 5; ++i) b += handle[i].size() * 4;
+    return b;
+}
+
+// ---------------------------------------------------------------------------- camera.rs:44-81
+namespace {
+struct H3 { float x, y, z; };
+H3 sub(H3 a, H3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+H3 mul(float s, H3 a) { return {s * a.x, s * a.y, s * a.z}; }
+H3 divs(H3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+float dotp(H3 a, H3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+H3 crossp(H3 a, H3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+H3 norm(H3 a) { float inv = 1.0f / std::sqrt(dotp(a, a)); return {a.x * inv, a.y * inv, a.z * inv}; }
+f3 tof3(H3 a) { f3 r; r.x = a.x; r.y = a.y; r.z = a.z; return r; }
+}  // namespace
+
+void camera_new(const float from[3], const float at[3], const float vup[3], float vfov, float aspect, float aperture,
+                float focus_dist, float t0, float t1, CameraPod& out) {
+    float theta = vfov * (kPi / 180.0f);  // f32::to_radians
+    float h = std::tan(theta / 2.0f);
+    float viewport_height = 2.0f * h;
+    float viewport_width = aspect * viewport_height;
+    H3 lf{from[0], from[1], from[2]}, la{at[0], at[1], at[2]}, up{vup[0], vup[1], vup[2]};
+    H3 w = norm(sub(lf, la));
+    H3 u = norm(crossp(up, w));
+    H3 v = crossp(w, u);
+    H3 horizontal = mul(focus_dist * viewport_width, u);
+    H3 vertical = mul(focus_dist * viewport_height, v);
+    H3 llc = sub(sub(sub(lf, divs(horizontal, 2.0f)), divs(vertical, 2.0f)), mul(focus_dist, w));
+    out.origin = tof3(lf); out.horizontal = tof3(horizontal); out.vertical = tof3(vertical); out.llc = tof3(llc);
+    out.u = tof3(u); out.v = tof3(v);
+    out.lens_radius = aperture / 2.0f; out.time0 = t0; out.time1 = t1;
+}
+
+// ---------------------------------------------------------------------------- renderer.rs:242-296
+std::vector<TileRect> tile_layout(int W, int H, int tw, int th) {
+    std::vector<TileRect> tiles;
+    int n_h = W / tw, rem_h = W % tw, n_v = H / th, rem_v = H % th;
+    tiles.reserve((size_t)(n_h + 1) * (n_v + 1));
+    for (int ty = 0; ty < n_v; ++ty) {
+        for (int tx = 0; tx < n_h; ++tx) tiles.push_back({tw, th, tx * tw, ty * th});
+        if (rem_h > 0) tiles.push_back({rem_h, th, n_h * tw, ty * th});
+    }
+    if (rem_v > 0)
+        for (int tx = 0; tx < n_h; ++tx) tiles.push_back({tw, rem_v, tx * tw, n_v * th});
+    if (rem_h > 0 && rem_v > 0) tiles.push_back({rem_h, rem_v, n_h * tw, n_v * th});
+    return tiles;
+}
+std::vector<uint32_t> tile_pixel_order(int W, int H, int tw, int th, int rank, int world) {
+    std::vector<TileRect> tiles = tile_layout(W, H, tw, th);
+    std::vector<uint32_t> order;
+    order.reserve((size_t)W * H / (world > 1 ? world : 1) + 64);
+    for (size_t ti = 0; ti < tiles.size(); ++ti) {
+        if (world > 1 && (int)(ti % (size_t)world) != rank) continue;
+        const TileRect& t = tiles[ti];
+        for (int y = 0; y < t.height; ++y)
+            for (int x = 0; x < t.width; ++x) order.push_back((uint32_t)((t.y0 + y) * W + (t.x0 + x)));
+    }
+    return order;
+}
+
+}  // namespace shim

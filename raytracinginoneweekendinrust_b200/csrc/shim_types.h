@@ -1,0 +1,113 @@
+// shim_types.h — plain-old-data shared by the host flattener and the sm_100a kernels.
+//
+// HBM layout of a committed scene (see DESIGN.md "Data layout"):
+//   nodes      DevNode[]      64 B/node: both child boxes + child refs + parent + leaf rank
+//   sph        double[4*n]    cx,cy,cz,r*r   (extend: f64 quadratic, geometry/sphere.rs:57-83)
+//   sph_s      f4[n]          cx,cy,cz,r + material in a side array (shade)
+//   msph       f4[3*n]        {c0,r} {c1,time0} {time1, mat, -, -}
+//   rect       f4[2*n]        {a0,a1,b0,b1} {k, axis, mat, -}
+//   tri        f4[3*n]        {p0,mat} {e1,-} {e2,-}
+//   cube       f4[2*n]        {min,mat} {max,-}
+//   objects    DevObject[]    the flattened top-level HittableList, in list order
+//   materials  f4[2*n], textures f4[2*n], image / perlin byte blobs
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define SHIM_HD __host__ __device__ __forceinline__
+#else
+#define SHIM_HD inline
+#endif
+
+namespace shim {
+
+struct f3 { float x, y, z; };
+struct alignas(16) f4 { float x, y, z, w; };
+struct alignas(16) i4 { int x, y, z, w; };
+
+SHIM_HD int f2i(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+SHIM_HD float i2f(int i) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+
+enum PrimType { PT_SPHERE = 0, PT_MSPHERE = 1, PT_RECT = 2, PT_TRI = 3, PT_CUBE = 4, PT_NONE = 7 };
+enum MatKind { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4, MAT_KINDS = 5 };
+enum TexKind { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_MARBLE = 2, TEX_IMAGE = 3 };
+enum { STAGE_CAMERA = 0, STAGE_INTERSECT = 1, STAGE_SCATTER = 2 };
+// mirror shim_status in include/shimmer_b200.h
+enum { SHIM_ERR_INVALID_ = -1, SHIM_ERR_UNSUPPORTED_ = -2, SHIM_ERR_CUDA_ = -3, SHIM_ERR_STATE_ = -4 };
+enum { SHIM_MAX_BVH_HEIGHT = 38 };  // traversal stack is 40 entries
+
+// primitive reference: type in the top 4 bits, index below
+SHIM_HD uint32_t prim_ref(int type, uint32_t index) { return ((uint32_t)type << 28) | index; }
+SHIM_HD int prim_type(uint32_t ref) { return (int)(ref >> 28); }
+SHIM_HD uint32_t prim_index(uint32_t ref) { return ref & 0x0FFFFFFFu; }
+static const int CHILD_NONE = (int)~(((uint32_t)PT_NONE << 28));  // empty child slot
+
+// One BVH node = the reference's BvhNode (bvh.rs:229-236) with the same index, plus both
+// CHILD boxes so one 64-byte fetch decides both descents.
+struct alignas(16) DevNode {
+    f4 a;  // l.min.x l.min.y l.min.z l.max.x
+    f4 b;  // l.max.y l.max.z r.min.x r.min.y
+    f4 c;  // r.min.z r.max.x r.max.y r.max.z
+    i4 d;  // left ref, right ref (>=0 node, <0 ~prim_ref), parent, left-to-right rank of the first primitive child
+};
+
+enum ObjFlags { OBJ_TRANSLATE = 1, OBJ_ROTATE = 2, OBJ_MEDIUM = 4, OBJ_PREDICTOR = 8 };
+enum ObjKind { OBJ_PRIM = 0, OBJ_BVH = 1 };
+
+struct alignas(16) DevObject {
+    int kind;      // OBJ_PRIM / OBJ_BVH
+    int ref;       // prim_ref, or root node index
+    int flags;
+    int handle;    // user handle reported for medium hits
+    float dx, dy, dz, sin_t;
+    float cos_t, neg_inv_density;
+    int phase_mat, predictor;
+    int n_nodes, pad0, pad1, pad2;
+};
+
+struct SceneView {
+    const DevNode* nodes;
+    const double* sph;      // 4 per sphere
+    const f4* sph_s;
+    const int* sph_mat;
+    const f4* msph;         // 3 per moving sphere
+    const f4* rect;         // 2 per rect
+    const f4* tri;          // 3 per triangle
+    const f4* cube;         // 2 per cube
+    const DevObject* objects;
+    const f4* materials;    // 2 per material
+    const f4* textures;     // 2 per texture
+    const uint8_t* images;
+    const uint8_t* perlin;
+    const int* handle[5];   // device prim index -> user handle, per PrimType
+    int n_objects;
+    int n_nodes;
+};
+
+struct CameraPod {  // camera.rs:6-27, derived on the host by Camera::new
+    f3 origin, horizontal, vertical, llc, u, v;
+    float lens_radius, time0, time1;
+};
+
+// closest-hit result, 16 B in the hit buffer
+struct Hit {
+    float t;
+    int obj;        // top-level object index, -1 = miss
+    uint32_t prim;  // prim_ref
+    int face;       // cube side 0..5
+};
+
+}  // namespace shim

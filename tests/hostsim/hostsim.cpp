@@ -1,0 +1,106 @@
+// hostsim.cpp — TEST HARNESS ONLY.  Compiles the product's __host__ __device__ arithmetic
+// (csrc/shim_device.h) and its flattener for the CPU, so that the device math can be checked
+// against the oracle in this GPU-less container before spending GPU time.  It is not part
+// of the package, is never loaded by it, and exists only under tests/.
+//
+// It links the product's CUDA-free builder entry points (shim_builder.cpp, shim_scene.cpp),
+// so scenes are recorded through the very same shim_* calls; only commit / trace / radiance
+// are replaced by serial loops over the shared inline functions.
+#include <cstring>
+#include <vector>
+
+#include "../../raytracinginoneweekendinrust_b200/csrc/shim_device.h"
+#include "../../raytracinginoneweekendinrust_b200/csrc/shim_internal.h"
+
+using namespace shim;
+
+void shim::device_state_release(DeviceState*) {}
+
+extern "C" __attribute__((visibility("default"))) int hs_commit(shim_scene* s);
+// the harness library answers shim_commit with the CPU-side flatten only (no device)
+extern "C" __attribute__((visibility("default"))) int shim_commit(shim_scene* s) { return hs_commit(s); }
+extern "C" __attribute__((visibility("default"))) int hs_commit(shim_scene* s) {
+    int rc = s->sb.flatten(s->flat);
+    if (rc < 0) return set_err(rc, s->sb.err);
+    s->has_media = false;
+    for (const DevObject& o : s->flat.objects) if (o.flags & OBJ_MEDIUM) s->has_media = true;
+    s->committed = true;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int hs_trace_closest(shim_scene* s, const float* rays, int64_t n, float t_min,
+                                                                      float t_max, uint64_t seed, int32_t* prim, float* t,
+                                                                      uint64_t* counters) {
+    SceneView sv = s->flat.view();
+    uint64_t nodes = 0, prims = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* q = rays + i * 7;
+        Ray r; r.o = mk3(q[0], q[1], q[2]); r.d = mk3(q[3], q[4], q[5]); r.time = q[6];
+        Rng rng;
+        rng_init(rng, (uint32_t)i, 0, seed);
+        rng_key(rng, 0, STAGE_INTERSECT);
+        TraceCounters tc; tc.nodes = 0; tc.prims = 0;
+        Hit h = closest_hit(sv, r, t_min, t_max, rng, &tc);
+        nodes += tc.nodes; prims += tc.prims;
+        prim[i] = hit_handle(sv, h);
+        t[i] = h.obj < 0 ? INFINITY : h.t;
+    }
+    if (counters) { counters[0] = (uint64_t)n; counters[1] = nodes; counters[2] = prims; }
+    return 0;
+}
+
+// the wavefront's per-path arithmetic, executed path by path (same order of operations as
+// wf_generate / wf_extend / wf_shade)
+extern "C" __attribute__((visibility("default"))) int hs_sample_radiance(shim_scene* s, const shim_camera* cam,
+                                                                        const shim_render_params* p, const int32_t* xys, int64_t n,
+                                                                        float* out_rgb, uint64_t* rays_out) {
+    SceneView sv = s->flat.view();
+    CameraPod c;
+    camera_new(cam->look_from, cam->look_at, cam->view_up, cam->vertical_fov, cam->aspect_ratio, cam->aperture, cam->focus_dist,
+               cam->time_start, cam->time_end, c);
+    uint64_t rays = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        int x = xys[i * 3], y = xys[i * 3 + 1];
+        uint32_t sample = (uint32_t)xys[i * 3 + 2], pixel = (uint32_t)(y * p->width + x);
+        Rng rng;
+        rng_init(rng, pixel, sample, p->seed);
+        rng_key(rng, 0, STAGE_CAMERA);
+        Ray r = camera_sample(c, x, y, p->width, p->height, rng);
+        f3 thr = mk3(1, 1, 1), L = mk3(0, 0, 0);
+        for (int bounce = 0; bounce < p->max_depth; ++bounce) {
+            rng_init(rng, pixel, sample, p->seed);
+            rng_key(rng, (uint32_t)bounce, STAGE_INTERSECT);
+            ++rays;
+            Hit h = closest_hit(sv, r, 0.001f, INFINITY, rng, nullptr);
+            if (h.obj < 0) { L = L + mk3(thr.x * p->background[0], thr.y * p->background[1], thr.z * p->background[2]); break; }
+            int mat = hit_material(sv, h);
+            int kind = mat_kind(sv, mat);
+            HitRec rec;
+            reconstruct_hit(sv, r, h, mat_needs_uv(sv, mat), rec);
+            if (kind == MAT_DIFFUSE_LIGHT) { L = L + thr * mat_emit(sv, mat, rec); break; }
+            rng_init(rng, pixel, sample, p->seed);
+            rng_key(rng, (uint32_t)bounce, STAGE_SCATTER);
+            f3 att; Ray out;
+            if (!mat_scatter(sv, kind, mat, r, rec, rng, att, out)) break;
+            thr = thr * att;
+            r = out;
+        }
+        out_rgb[i * 3] = L.x; out_rgb[i * 3 + 1] = L.y; out_rgb[i * 3 + 2] = L.z;
+    }
+    if (rays_out) *rays_out = rays;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) void hs_texture_value(shim_scene* s, int tex, float u, float v, const float* p,
+                                                                       float* out) {
+    SceneView sv = s->flat.view();
+    f3 c = tex_value(sv, tex, u, v, mk3(p[0], p[1], p[2]));
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
+}
+
+extern "C" __attribute__((visibility("default"))) void hs_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    Rng r;
+    r.pixel = ctr[0]; r.sample = ctr[1]; r.dim = ctr[2]; r.j = ctr[3] << 2; r.k0 = key[0]; r.k1 = key[1];
+    rng_refill(r);
+    out[0] = r.b0; out[1] = r.b1; out[2] = r.b2; out[3] = r.b3;
+}
