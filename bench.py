@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the path-tracing hot path on N B200s (one process per GPU).
+
+A *step* is one full render of the workload (BASELINE.json config C1 by default: Book-1
+random-spheres, 1200x800, 10 spp, depth 50) — every sample's camera ray generation, BVH
+traversal + intersection and scatter/shade, i.e. everything under Renderer::render
+(reference src/renderer.rs:42-105) except the PPM write.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C1] [--impl reference]
+
+N > 1 (launched by torch.distributed.run): sample-range sharding, weak scaling — every rank
+renders `spp` samples per pixel of its own absolute sample range over the full image, then one
+framebuffer reduce over NCCL; no collective inside the wavefront loop.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Mrays/s"
+
+
+# --------------------------------------------------------------------------------------------
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args):
+    from raytracinginoneweekendinrust_b200 import scenes
+    cfg = scenes.configs()[args.config]
+    spp = args.spp if args.spp > 0 else cfg.spp
+    W = args.width if args.width > 0 else cfg.width
+    H = args.height if args.height > 0 else cfg.height
+    return cfg, W, H, spp
+
+
+def scene_kwargs(cfg, args):
+    kw = dict(cfg.scene_kwargs)
+    if args.tris > 0 and cfg.scene in ("bunny", "gargoyle", "igea-hrpp"):
+        kw["n_tris"] = args.tris
+    return kw
+
+
+def config_dict(cfg, W, H, spp, args, extra=None):
+    d = {"workload": f"{cfg.key} {cfg.scene} {W}x{H} {spp}spp depth{cfg.max_depth}", "scene": cfg.scene, "width": W, "height": H,
+         "spp": spp, "max_depth": cfg.max_depth, "scene_seed": 1, "tile": "8x8",
+         "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# -------------------------------------------------------------------------------------------- CPU arm
+def run_cpu(args, steps, warmup, budget_s, threads=0):
+    """The reference's path on the host cores: the C++ restatement in oracle/ in reference mode
+    (recursive both-children traversal, per-node divides, f64 spheres, recursion, 8x8 tiles pulled by
+    one thread per logical core), xorshift RNG standing in for thread_rng.  Each step renders a bounded
+    sample of the workload (fewer spp; throughput does not depend on spp) sized from a 1-spp calibration
+    so that warmup + steps stay within ``budget_s`` seconds."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import support
+    from raytracinginoneweekendinrust_b200 import scenes
+    cfg, W, H, spp = workload(args)
+    o = support.OracleScene()
+    info = scenes.build(o, cfg.scene, seed=1, **scene_kwargs(cfg, args))
+
+    def params(n_spp):
+        return o.params(W, H, n_spp, cfg.max_depth, background=info.background, seed=0, rng_fast=True, iterative=False,
+                        threads=threads, use_predictors=info.predictors)
+
+    _, cal = o.render(cfg.camera, params(1))
+    per_spp = max(cal.seconds, 1e-4)
+    cpu_spp = int(max(1, min(spp, budget_s / max(1, steps + warmup) / per_spp)))
+    times, best = [], None
+    for i in range(warmup + steps):
+        _, st = o.render(cfg.camera, params(cpu_spp))
+        if i >= warmup:
+            times.append(st.seconds)
+            best = st
+    sec = float(np.mean(times))
+    return {"mrays": best.rays / sec / 1e6, "samples_per_s": best.samples / sec, "seconds": sec, "threads": int(best.threads),
+            "rays": int(best.rays), "sample": f"{cfg.scene} {W}x{H} at {cpu_spp} spp (of {spp}), depth {cfg.max_depth}, "
+                                              f"{steps} timed render(s) after {warmup} warm-up",
+            "nodes_per_ray": best.node_visits / max(1, best.rays), "prims_per_ray": best.prim_tests / max(1, best.rays)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, W, H, spp = workload(args)
+    r = run_cpu(args, args.steps, args.warmup, budget_s=120.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["mrays"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (+f64 sphere quadratic)", "data": "synthetic",
+            "config": config_dict(cfg, W, H, spp, args),
+            "samples_per_s": r["samples_per_s"],
+            "cpu_baseline": {"value": r["mrays"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference is Rust (no rustc here): C++ restatement in oracle/ run in reference mode on the host cores"}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------- GPU arm
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from raytracinginoneweekendinrust_b200 import api, capi, scenes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this backend has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, W, H, spp = workload(args)
+    scene = api.Scene()
+    info = scenes.build(scene, cfg.scene, seed=1, **scene_kwargs(cfg, args))
+    flags = capi.RENDER_RAW_SUM | capi.RENDER_PROFILE | (capi.RENDER_PREDICTORS if info.predictors else 0)
+    total_spp = spp * world
+    # weak scaling: rank r renders absolute samples [r*spp, (r+1)*spp) of a total_spp-sample image
+    params = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
+                             sample_count=spp, flags=flags, pool_paths=args.pool)
+    fb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        st = scene.render_device(cfg.camera, params, fb.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+        flush.zero_()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stats = []
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        stats.append(step())
+        ev[k][1].record(stream)
+        flush.zero_()  # L2 flush between timed steps (outside the event pair)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else {}
+    ms = [a.elapsed_time(b) for a, b in ev]
+    tot_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    rays = torch.tensor([float(sum(s.rays for s in stats))], dtype=torch.float64, device=dev)
+    samples = torch.tensor([float(sum(s.samples for s in stats))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+        dist.all_reduce(samples, op=dist.ReduceOp.SUM)
+    tot_s = float(tot_ms.item()) / 1e3
+    value = float(rays.item()) / tot_s / 1e6
+    samples_per_s = float(samples.item()) / tot_s
+
+    # ---- e2e: the C-ABI call with HOST buffers: commit (flatten + H2D of the scene) + render + D2H framebuffer
+    e2e_ms, h2d, d2h = [], 0, W * H * 3 * 4
+    e2e_rays = 0
+    p_e2e = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
+                            sample_count=spp, flags=capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0),
+                            pool_paths=args.pool)
+    for k in range(args.e2e_steps + 1):
+        s2 = api.Scene()
+        scenes.SCENES[cfg.scene](s2, seed=1, **scene_kwargs(cfg, args))  # host-side recording (untimed)
+        barrier()
+        t0 = time.perf_counter()
+        s2.commit()
+        _, st2 = s2.render(cfg.camera, p_e2e)
+        dt = time.perf_counter() - t0
+        if k > 0:  # first one warms the allocator / pool
+            e2e_ms.append(dt * 1e3)
+            e2e_rays += st2.rays
+        h2d = s2.device_bytes() + W * H * 4
+        s2.close()
+    e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
+    e2e_r = torch.tensor([float(e2e_rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_r, op=dist.ReduceOp.SUM)
+    e2e_value = float(e2e_r.item()) / (float(e2e_t.item()) / 1e3) / 1e6
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (wf_extend): algorithmic bytes per ray x rays / its event time
+        st_cnt = scene.render_device(cfg.camera, api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0,
+                                                                sample_begin=0, sample_count=min(spp, 2),
+                                                                flags=capi.RENDER_RAW_SUM | capi.RENDER_COUNT_NODES, pool_paths=args.pool),
+                                     fb.data_ptr(), stream.cuda_stream)
+        nodes_per_ray = st_cnt.node_visits / max(1, st_cnt.rays)
+        prims_per_ray = st_cnt.prim_tests / max(1, st_cnt.rays)
+        prim_bytes = {"random-spheres": 32, "cornell-smoke": 32, "showcase": 32}.get(cfg.scene, 48)
+        bytes_per_ray = nodes_per_ray * 64 + prims_per_ray * prim_bytes + 128
+        ext_ms = sum(s.extend_ms for s in stats)
+        ext_launch = sum(s.extend_launches for s in stats)
+        rays_rank0 = sum(s.rays for s in stats)
+        peak, peak_src, sm_max = load_peaks()
+        achieved = bytes_per_ray * rays_rank0 / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
+        sm_clk = (clocks.get("sm_mhz") or sm_max) * 1e6
+        inst_per_ray = nodes_per_ray * 2 * 30 + prims_per_ray * 90 + 150  # SURVEY §8d budget (two boxes per 64 B node, f64 sphere x2)
+        issue_peak = 148 * 128 * sm_clk / inst_per_ray / 1e6
+        roofline = {"bound": "hbm", "kernel": "wf_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "prims_per_ray": prims_per_ray,
+                    "extend_ms_per_step": ext_ms / args.steps, "extend_share_of_step": ext_ms / sum(ms),
+                    "extend_launches_per_step": ext_launch / args.steps,
+                    "note": "scene data is L1/L2 resident (KB-sized); the binding ceiling is instruction issue, see issue_roofline",
+                    "issue_roofline": {"budget_inst_per_ray": inst_per_ray, "sm_mhz": sm_clk / 1e6,
+                                       "peak_mrays": issue_peak, "achieved_mrays_extend_only": rays_rank0 / (ext_ms / 1e3) / 1e6 if ext_ms > 0 else None,
+                                       "frac": (rays_rank0 / (ext_ms / 1e3) / 1e6) / issue_peak if ext_ms > 0 else None}}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            c = run_cpu(args, args.steps_cpu, args.warmup_cpu, budget_s=25.0)
+            cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": c["threads"], "kind": "port", "sample": c["sample"],
+                   "samples_per_s": c["samples_per_s"], "ref_nodes_per_ray": c["nodes_per_ray"], "ref_prims_per_ray": c["prims_per_ray"]}
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": float(tot_ms.item()) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (+f64 sphere quadratic)", "data": "synthetic",
+                "config": config_dict(cfg, W, H, spp, args, {"sharding": f"sample-range x{world}", "pool_paths": args.pool or (1 << 21),
+                                                             "scene_device_bytes": scene.device_bytes()}),
+                "samples_per_s": samples_per_s, "rays_per_step": float(rays.item()) / args.steps,
+                "wall_s_timed_region": wall,
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": float(e2e_t.item()) / max(1, len(e2e_ms)),
+                        "what": "shim_commit (flatten + scene H2D) + shim_render into a host framebuffer (D2H), host timer"},
+                "gpu_launches": int(sum(s.kernel_launches for s in stats)),
+                "iterations_per_step": float(np.mean([s.iterations for s in stats])),
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C1")
+    ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--tris", type=int, default=0)
+    ap.add_argument("--pool", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--steps-cpu", type=int, default=2)
+    ap.add_argument("--warmup-cpu", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,7 +106,8 @@ typedef struct shim_camera {
 } shim_camera;
 
 /* ---- render: Renderer::render, renderer.rs:42-105 -------------------------------------- */
-enum { SHIM_RENDER_RAW_SUM = 1, SHIM_RENDER_PREDICTORS = 2, SHIM_RENDER_COUNT_NODES = 4 };
+enum { SHIM_RENDER_RAW_SUM = 1, SHIM_RENDER_PREDICTORS = 2, SHIM_RENDER_COUNT_NODES = 4,
+       SHIM_RENDER_PROFILE = 8 /* CUDA events around every wf_extend launch -> stats.extend_ms */ };
 typedef struct shim_render_params {
     int32_t width, height;         /* Renderer::new */
     int32_t samples_per_pixel;     /* divisor of the mean */
@@ -129,8 +130,8 @@ typedef struct shim_stats {
     uint64_t kernel_launches;
     uint64_t iterations;
     double device_ms;              /* CUDA events around the wavefront loop */
-    double extend_ms, shade_ms, generate_ms; /* per-kernel-class event sums (only with SHIM_PROFILE=1) */
-    uint64_t extend_launches;
+    double extend_ms, shade_ms, generate_ms; /* event sums per kernel class (extend only, with SHIM_RENDER_PROFILE) */
+    uint64_t extend_launches;      /* wf_extend launches that had rays, covered by extend_ms */
 } shim_stats;
 
 /* host framebuffer: width*height*3 floats, linear radiance, row-major, y = 0 is the bottom row

@@ -57,6 +57,7 @@ class Camera(C.Structure):
 RENDER_RAW_SUM = 1
 RENDER_PREDICTORS = 2
 RENDER_COUNT_NODES = 4
+RENDER_PROFILE = 8
 
 
 class RenderParams(C.Structure):

@@ -73,6 +73,7 @@ struct Wavefront {
     uint32_t* h_flags = nullptr;  // pinned: done flag readbacks
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr};
     int grid_extend = 0, grid_shade = 0, grid_generate = 0;
+    std::vector<cudaEvent_t> prof;  // event pairs around wf_extend launches (SHIM_RENDER_PROFILE)
     void release() {
         for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); samp[i].release(); }
         hit.release(); cnt.release(); accum.release(); pix_table.release();
@@ -83,6 +84,8 @@ struct Wavefront {
         if (ev1) cudaEventDestroy(ev1);
         for (auto& e : ev_chunk) if (e) cudaEventDestroy(e);
         ev0 = ev1 = ev_chunk[0] = ev_chunk[1] = nullptr;
+        for (auto& e : prof) cudaEventDestroy(e);
+        prof.clear();
         pool = 0;
     }
 };
@@ -215,6 +218,14 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     CU(cudaEventRecord(w.ev0, st));
 
     uint64_t launches = 0;
+    const bool profile = (p.flags & SHIM_RENDER_PROFILE) != 0;
+    size_t prof_used = 0;
+    const size_t prof_cap = 2 * 2048;
+    if (profile && w.prof.size() < prof_cap) {
+        size_t have = w.prof.size();
+        w.prof.resize(prof_cap);
+        for (size_t i = have; i < prof_cap; ++i) CU(cudaEventCreate(&w.prof[i]));
+    }
     if (k.total_samples > 0 && p.max_depth > 0) {
         // iterations are enqueued in chunks; the done flag of chunk c is read back while chunk c+1 runs
         const int chunk = 8;
@@ -224,7 +235,10 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
             for (int it = 0; it < chunk; ++it) {
                 wf_begin<<<1, 32, 0, st>>>(k, cur);
                 wf_generate<<<w.grid_generate, 256, 0, st>>>(k, cur);
+                const bool rec = profile && prof_used + 2 <= prof_cap;
+                if (rec) CU(cudaEventRecord(w.prof[prof_used], st));
                 wf_extend<<<w.grid_extend, 256, 0, st>>>(k, cur);
+                if (rec) { CU(cudaEventRecord(w.prof[prof_used + 1], st)); prof_used += 2; }
                 wf_shade<MAT_LAMBERTIAN><<<w.grid_shade, 256, 0, st>>>(k, cur);
                 wf_shade<MAT_METAL><<<w.grid_shade, 256, 0, st>>>(k, cur);
                 wf_shade<MAT_DIELECTRIC><<<w.grid_shade, 256, 0, st>>>(k, cur);
@@ -263,6 +277,14 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
         stats->device_ms = ms;
+        // per-launch durations of wf_extend while it had work: launches past the done flag are skipped
+        uint64_t it_done = stats->iterations;
+        for (size_t i = 0; i + 1 < prof_used && i / 2 < it_done; i += 2) {
+            float e = 0;
+            CU(cudaEventElapsedTime(&e, w.prof[i], w.prof[i + 1]));
+            stats->extend_ms += e;
+            stats->extend_launches += 1;
+        }
     }
     return SHIM_OK;
 }

@@ -1,0 +1,114 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import support
+from raytracinginoneweekendinrust_b200 import api, capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+SMALL = {"bunny": {"n_tris": 3000}, "gargoyle": {"n_tris": 6000}, "igea-hrpp": {"n_tris": 6000, "predictor": False},
+         "showcase": {"predictors": False}}
+CAMERAS = {
+    "random-spheres": scenes.configs()["C1"].camera,
+    "random-moving-spheres": capi.Camera.new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.1, 10.0, 0.0, 1.0),
+    "two-spheres": capi.Camera.new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.0, 10.0),
+    "marble": capi.Camera.new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.0, 10.0),
+    "earth": capi.Camera.new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.0, 10.0),
+    "simple-lights": capi.Camera.new((26, 3, 6), (0, 2, 0), (0, 1, 0), 20.0, 1.5, 0.0, 10.0),
+    "cornell": scenes.cornell_camera(1.0),
+    "cornell-smoke": scenes.cornell_camera(1.0),
+    "showcase": scenes.configs()["C4"].camera,
+    "bunny": scenes.cornell_camera(1.5),
+    "gargoyle": scenes.cornell_camera(1.5),
+    "igea-hrpp": scenes.cornell_camera(1.5),
+}
+
+
+def build_pair(name, seed=1):
+    g = api.Scene()
+    info = scenes.build(g, name, seed=seed, **SMALL.get(name, {}))
+    o = support.OracleScene()
+    scenes.build(o, name, seed=seed, **SMALL.get(name, {}))
+    return g, o, info
+
+
+@pytest.mark.parametrize("name", list(scenes.SCENES))
+def test_closest_hit_gate1(name):
+    """Gate 1: same primitive id, t within 1e-5 relative, on camera + bounce rays of the scene."""
+    g, o, info = build_pair(name)
+    cam = CAMERAS[name]
+    W, H, spp = 160, 120, 4
+    po = o.params(W, H, spp, 50, background=info.background, seed=3, iterative=True)
+    rays = o.record_path_rays(cam, po, support.random_xys(W, H, spp, 6000, seed=1), 60000)
+    assert len(rays) > 6000
+    p_ref, t_ref = o.trace_closest(rays, seed=3)
+    p_gpu, t_gpu = g.trace_closest(rays, seed=3)
+    hit = p_ref >= 0
+    mism = p_ref != p_gpu
+    # volumes draw ln(U): device logf differs from glibc by an ulp, which can flip an accept at a boundary
+    allowed = 0 if name not in ("cornell-smoke", "showcase") else max(2, len(rays) // 20000)
+    assert mism.sum() <= allowed, f"{mism.sum()} primitive id mismatches"
+    ok = hit & ~mism
+    rel = np.abs(t_ref[ok] - t_gpu[ok]) / np.maximum(np.abs(t_ref[ok]), 1e-30)
+    assert rel.max() <= 1e-5
+    assert np.isinf(t_gpu[~hit & ~mism]).all()
+
+
+@pytest.mark.parametrize("name", list(scenes.SCENES))
+def test_render_matches_oracle_same_stream(name):
+    """Gate 2 in miniature: identical Philox streams on both sides -> images agree far below MC noise."""
+    g, o, info = build_pair(name)
+    cam = CAMERAS[name]
+    W, H, spp, depth = 64, 48, 8, 50
+    img_gpu, st = g.render(cam, api.make_params(W, H, spp, depth, background=info.background, seed=5))
+    img_ref, so = o.render(cam, o.params(W, H, spp, depth, background=info.background, seed=5))
+    assert st.samples == W * H * spp
+    diff = np.abs(img_gpu - img_ref)
+    outlier = diff.max(axis=2) > 1e-3
+    # paths that depend on logf / sinf / acosf (volumes, marble, image uv) can flip where the device libm and
+    # glibc differ by an ulp; such pixels are the stated outliers.  Everything else is the same path.
+    allowed = 0 if name in ("random-spheres", "two-spheres", "cornell", "bunny", "gargoyle", "igea-hrpp") else max(2, W * H // 500)
+    assert outlier.sum() <= allowed, f"{outlier.sum()} outlier pixels"
+    rmse = float(np.sqrt(np.mean(diff[~outlier] ** 2)))
+    assert rmse <= 1e-5, f"rmse {rmse} over non-outlier pixels"
+    assert abs(int(st.rays) - int(so.rays)) <= max(4, so.rays // 2000), (st.rays, so.rays)
+
+
+def test_sample_range_and_tile_sharding_compose():
+    """Sample-range shards and tile shards sum to the single-call image."""
+    g, o, info = build_pair("random-spheres")
+    cam = CAMERAS["random-spheres"]
+    W, H, spp = 70, 50, 6
+    full, _ = g.render(cam, api.make_params(W, H, spp, 50, background=info.background, seed=9, flags=capi.RENDER_RAW_SUM))
+    a, _ = g.render(cam, api.make_params(W, H, spp, 50, background=info.background, seed=9, sample_begin=0, sample_count=2, flags=capi.RENDER_RAW_SUM))
+    b, _ = g.render(cam, api.make_params(W, H, spp, 50, background=info.background, seed=9, sample_begin=2, sample_count=4, flags=capi.RENDER_RAW_SUM))
+    np.testing.assert_allclose(a + b, full, rtol=1e-5, atol=1e-6)
+    t0, _ = g.render(cam, api.make_params(W, H, spp, 50, background=info.background, seed=9, tile_rank=0, tile_world=2, flags=capi.RENDER_RAW_SUM))
+    t1, _ = g.render(cam, api.make_params(W, H, spp, 50, background=info.background, seed=9, tile_rank=1, tile_world=2, flags=capi.RENDER_RAW_SUM))
+    np.testing.assert_allclose(t0 + t1, full, rtol=1e-5, atol=1e-6)
+    assert (t0.sum(axis=2) > 0).sum() + (t1.sum(axis=2) > 0).sum() <= W * H + 0
+
+
+def test_small_pool_regeneration_matches():
+    """A pool far smaller than the sample count (many regeneration rounds) gives the same image."""
+    g, o, info = build_pair("cornell")
+    cam = CAMERAS["cornell"]
+    W, H, spp = 48, 48, 8
+    big, _ = g.render(cam, api.make_params(W, H, spp, 50, seed=2))
+    small, st = g.render(cam, api.make_params(W, H, spp, 50, seed=2, pool_paths=1024))
+    assert st.iterations > 18
+    np.testing.assert_allclose(small, big, rtol=1e-5, atol=1e-6)
+
+
+def test_depth_limit_and_empty_cases():
+    g, o, info = build_pair("random-spheres")
+    cam = CAMERAS["random-spheres"]
+    img, st = g.render(cam, api.make_params(32, 24, 2, 0, background=info.background))
+    assert st.rays == 0 and not img.any()          # ray.rs:39-42: depth 0 -> black
+    img1, st1 = g.render(cam, api.make_params(32, 24, 2, 1, background=info.background))
+    ref1, _ = o.render(cam, o.params(32, 24, 2, 1, background=info.background))
+    assert st1.rays == 32 * 24 * 2
+    np.testing.assert_allclose(img1, ref1, atol=1e-6)
+    p, t = g.trace_closest(np.zeros((0, 7), np.float32))
+    assert len(p) == 0 and len(t) == 0
