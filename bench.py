@@ -242,14 +242,18 @@ def main_gpu(args):
     p_e2e = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
                             sample_count=spp, flags=capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0),
                             pool_paths=args.pool)
-    for k in range(args.e2e_steps + 1):
+    for k in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         s2 = api.Scene()
         scenes.SCENES[cfg.scene](s2, seed=1, **scene_kwargs(cfg, args))  # host-side recording (untimed)
         barrier()
         t0 = time.perf_counter()
         s2.commit()
+        tc = time.perf_counter()
         _, st2 = s2.render(cfg.camera, p_e2e)
         dt = time.perf_counter() - t0
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"e2e step {k}: commit {1e3 * (tc - t0):.2f} ms, render {1e3 * (time.perf_counter() - tc):.2f} ms "
+                  f"(device {st2.device_ms:.2f} ms, {st2.iterations} iterations)", file=sys.stderr)
         if k > 0:  # first one warms the allocator / pool
             e2e_ms.append(dt * 1e3)
             e2e_rays += st2.rays
@@ -260,7 +264,7 @@ def main_gpu(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_r, op=dist.ReduceOp.SUM)
-    e2e_value = float(e2e_r.item()) / (float(e2e_t.item()) / 1e3) / 1e6
+    e2e_value = float(e2e_r.item()) / (float(e2e_t.item()) / 1e3) / 1e6 if e2e_ms else None
 
     if rank == 0:
         # ---- roofline of the dominant kernel (wf_extend): algorithmic bytes per ray x rays / its event time
@@ -297,7 +301,7 @@ def main_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(tot_ms.item()) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (+f64 sphere quadratic)", "data": "synthetic",
-                "config": config_dict(cfg, W, H, spp, args, {"sharding": f"sample-range x{world}", "pool_paths": args.pool or (1 << 21),
+                "config": config_dict(cfg, W, H, spp, args, {"sharding": f"sample-range x{world}", "pool_paths": args.pool or (1 << 22),
                                                              "scene_device_bytes": scene.device_bytes()}),
                 "samples_per_s": samples_per_s, "rays_per_step": float(rays.item()) / args.steps,
                 "wall_s_timed_region": wall,

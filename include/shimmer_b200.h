@@ -91,6 +91,12 @@ int shim_rotate_y(shim_scene* s, int hittable, float degrees);
 int shim_constant_medium(shim_scene* s, int boundary, float density, int albedo_tex);
 /* the `world: &HittableList` argument of render, in list order */
 int shim_world_add(shim_scene* s, int hittable);
+/* Scene options, set before shim_commit.  SHIM_OPT_DEVICE_BVH: which tree the kernels walk for each
+ * Bvh — a binned-SAH rebuild of its primitive list (default; results do not depend on the tree) or the
+ * recorded bvh.rs topology (node indices then equal the reference's, e.g. for HRPP comparisons). */
+enum { SHIM_OPT_DEVICE_BVH = 1 };
+enum { SHIM_DEVICE_BVH_SAH = 0, SHIM_DEVICE_BVH_REFERENCE = 1 };
+int shim_scene_set_option(shim_scene* s, int option, int value);
 /* flattens the world into SoA arrays and uploads them to the current CUDA device */
 int shim_commit(shim_scene* s);
 

@@ -126,6 +126,9 @@ def bind_builder(lib: C.CDLL, prefix: str) -> None:
     for name in ("bvh_info", "bvh_nodes"):
         fn = getattr(lib, prefix + name)
         fn.restype = _I
+    if prefix == "shim_":
+        lib.shim_scene_set_option.restype = _I
+        lib.shim_scene_set_option.argtypes = [_P, _I, _I]
     getattr(lib, prefix + "bvh_info").argtypes = [_P, _I, _P, _P, _P]
     getattr(lib, prefix + "bvh_nodes").argtypes = [_P, _I, _P, _P, _P, _P]
 
@@ -249,6 +252,11 @@ class SceneHandle:
 
     def constant_medium_color(self, boundary, density, rgb):
         return self.constant_medium(boundary, density, self.texture_solid(*rgb))
+
+    def set_device_bvh(self, reference: bool):
+        """Walk the recorded bvh.rs topology on the device (True) or the SAH rebuild (False, default)."""
+        if self.prefix == "shim_":
+            self._call("scene_set_option", 1, 1 if reference else 0)
 
     def world_add(self, h): return self._call("world_add", h)
     def commit(self): return self._call("commit")

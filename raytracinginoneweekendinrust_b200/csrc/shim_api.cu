@@ -52,13 +52,16 @@ struct DeviceScene {
     DevBuf<int> sph_mat;
     DevBuf<DevObject> objects;
     DevBuf<uint8_t> images, perlin;
-    DevBuf<int> handle[5];
+    DevBuf<int> handle[5], rank[5], leaf[5];
     SceneView view;
+    SmemLayout smem;
     uint64_t bytes = 0;
     void release() {
         nodes.release(); sph.release(); sph_s.release(); msph.release(); rect.release(); tri.release(); cube.release();
         materials.release(); textures.release(); sph_mat.release(); objects.release(); images.release(); perlin.release();
         for (auto& h : handle) h.release();
+        for (auto& h : rank) h.release();
+        for (auto& h : leaf) h.release();
     }
 };
 
@@ -72,7 +75,8 @@ struct Wavefront {
     uint32_t npix = 0;
     uint32_t* h_flags = nullptr;  // pinned: done flag readbacks
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr};
-    int grid_extend = 0, grid_shade = 0, grid_generate = 0;
+    int grid_extend_smem = 0, grid_extend_gmem = 0, grid_shade = 0, grid_generate = 0, grid_tail = 0;
+    int max_smem = 0;
     std::vector<cudaEvent_t> prof;  // event pairs around wf_extend launches (SHIM_RENDER_PROFILE)
     void release() {
         for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); samp[i].release(); }
@@ -94,16 +98,18 @@ struct Wavefront {
 
 struct shim::DeviceState {
     DeviceScene scene;
-    Wavefront wf;
     int device = -1;
     int sm_count = 0;
 };
 void shim::device_state_release(DeviceState* d) {
     if (!d) return;
     d->scene.release();
-    d->wf.release();
     delete d;
 }
+
+// The wavefront pool (ray queues, hit buffer, material queues, counters) is per device, not per
+// scene: scenes come and go (one per render call in the e2e path) while the pool is reused.
+static Wavefront g_wf[64];
 
 // ------------------------------------------------------------------------------------------ commit
 static int ensure_device(shim_scene* s) {
@@ -131,15 +137,33 @@ SHIM_API int shim_commit(shim_scene* s) {
     CU(d.msph.upload(f.msph)); CU(d.rect.upload(f.rect)); CU(d.tri.upload(f.tri)); CU(d.cube.upload(f.cube));
     CU(d.objects.upload(f.objects)); CU(d.materials.upload(f.materials)); CU(d.textures.upload(f.textures));
     CU(d.images.upload(f.images)); CU(d.perlin.upload(f.perlin));
-    for (int i = 0; i < 5; ++i) CU(d.handle[i].upload(f.handle[i]));
+    for (int i = 0; i < 5; ++i) { CU(d.handle[i].upload(f.handle[i])); CU(d.rank[i].upload(f.rank[i])); CU(d.leaf[i].upload(f.leaf[i])); }
     SceneView& v = d.view;
     memset(&v, 0, sizeof v);
     v.nodes = d.nodes.p; v.sph = d.sph.p; v.sph_s = d.sph_s.p; v.sph_mat = d.sph_mat.p; v.msph = d.msph.p; v.rect = d.rect.p;
     v.tri = d.tri.p; v.cube = d.cube.p; v.objects = d.objects.p; v.materials = d.materials.p; v.textures = d.textures.p;
     v.images = d.images.p; v.perlin = d.perlin.p;
-    for (int i = 0; i < 5; ++i) v.handle[i] = d.handle[i].p;
+    for (int i = 0; i < 5; ++i) { v.handle[i] = d.handle[i].p; v.rank[i] = d.rank[i].p; v.leaf[i] = d.leaf[i].p; }
     v.n_objects = (int)f.objects.size(); v.n_nodes = (int)f.nodes.size();
     d.bytes = f.bytes();
+    {   // shared-memory image of what wf_extend walks; total = 0 when it cannot fit any sm_100a block
+        SmemLayout& L = d.smem;
+        memset(&L, 0, sizeof L);
+        uint32_t off = 0;
+        auto place = [&](uint32_t& o, uint32_t& b, size_t bytes) { o = off; b = (uint32_t)bytes; off += (uint32_t)((bytes + 127) & ~(size_t)127); };
+        size_t tot = f.nodes.size() * sizeof(DevNode) + f.sph.size() * 8 + (f.msph.size() + f.rect.size() + f.tri.size() + f.cube.size()) * 16 +
+                     f.objects.size() * sizeof(DevObject);
+        if (tot <= 220 * 1024) {
+            place(L.off_nodes, L.bytes_nodes, f.nodes.size() * sizeof(DevNode));
+            place(L.off_sph, L.bytes_sph, f.sph.size() * 8);
+            place(L.off_msph, L.bytes_msph, f.msph.size() * 16);
+            place(L.off_rect, L.bytes_rect, f.rect.size() * 16);
+            place(L.off_tri, L.bytes_tri, f.tri.size() * 16);
+            place(L.off_cube, L.bytes_cube, f.cube.size() * 16);
+            place(L.off_objects, L.bytes_objects, f.objects.size() * sizeof(DevObject));
+            L.total = off;
+        }
+    }
     s->has_media = false;
     for (const DevObject& o : f.objects) if (o.flags & OBJ_MEDIUM) s->has_media = true;
     s->committed = true;
@@ -148,8 +172,8 @@ SHIM_API int shim_commit(shim_scene* s) {
 
 // ------------------------------------------------------------------------------------------ render
 static int wf_prepare(shim_scene* s, const shim_render_params& p) {
-    Wavefront& w = s->dev->wf;
-    uint32_t pool = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 21);
+    Wavefront& w = g_wf[s->dev->device & 63];
+    uint32_t pool = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 22);
     const char* env = getenv("SHIM_POOL_PATHS");
     if (p.pool_paths <= 0 && env && atoi(env) > 0) pool = (uint32_t)atoi(env);
     pool = (pool + 31u) & ~31u;
@@ -161,13 +185,20 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         if (!w.h_flags) CU(cudaMallocHost(&w.h_flags, 64 * sizeof(uint32_t)));
         if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); CU(cudaEventCreate(&w.ev_chunk[0])); CU(cudaEventCreate(&w.ev_chunk[1])); }
         w.pool = pool;
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_extend, 256, 0));
-        w.grid_extend = s->dev->sm_count * (per_sm > 0 ? per_sm : 1);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_shade<MAT_LAMBERTIAN>, 256, 0));
-        w.grid_shade = s->dev->sm_count * (per_sm > 0 ? per_sm : 1);
+        int sms = s->dev->sm_count, per_sm = 0;
+        CU(cudaDeviceGetAttribute(&w.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->dev->device));
+        CU(cudaFuncSetAttribute(wf_extend<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        w.grid_extend_smem = sms;  // one persistent block per SM owns the shared-memory copy of the scene
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_extend<false, false, false>, SHIM_EXTEND_THREADS, 0));
+        w.grid_extend_gmem = sms * (per_sm > 0 ? per_sm : 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_shade, 256, 0));
+        w.grid_shade = sms * (per_sm > 0 ? per_sm : 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
-        w.grid_generate = s->dev->sm_count * (per_sm > 0 ? per_sm : 1);
+        w.grid_generate = sms * (per_sm > 0 ? per_sm : 1);
+        w.grid_tail = sms;
     }
     size_t fb = (size_t)p.width * p.height * 3;
     if (w.accum.n != fb) CU(w.accum.alloc(fb));
@@ -180,6 +211,16 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         memcpy(w.pt_key, key, sizeof key);
     }
     return SHIM_OK;
+}
+
+static void launch_extend(const WfParams& k, int cur, int grid, uint32_t smem, cudaStream_t st) {
+    const bool S = smem != 0, C = k.count_nodes != 0, M = k.has_media != 0;
+#define SHIM_LAUNCH(SS, CC, MM) wf_extend<SS, CC, MM><<<grid, SHIM_EXTEND_THREADS, smem, st>>>(k, cur)
+    if (S) { if (C) { if (M) SHIM_LAUNCH(true, true, true); else SHIM_LAUNCH(true, true, false); }
+             else   { if (M) SHIM_LAUNCH(true, false, true); else SHIM_LAUNCH(true, false, false); } }
+    else   { if (C) { if (M) SHIM_LAUNCH(false, true, true); else SHIM_LAUNCH(false, true, false); }
+             else   { if (M) SHIM_LAUNCH(false, false, true); else SHIM_LAUNCH(false, false, false); } }
+#undef SHIM_LAUNCH
 }
 
 SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shim_render_params* pp, float* d_out, shim_stats* stats,
@@ -195,7 +236,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = wf_prepare(s, p);
     if (rc < 0) return rc;
-    Wavefront& w = s->dev->wf;
+    Wavefront& w = g_wf[s->dev->device & 63];
 
     WfParams k;
     memset(&k, 0, sizeof k);
@@ -212,6 +253,11 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     k.pool = w.pool; k.width = p.width; k.height = p.height; k.max_depth = p.max_depth; k.sample_begin = p.sample_begin;
     k.bg[0] = p.background[0]; k.bg[1] = p.background[1]; k.bg[2] = p.background[2];
     k.seed = p.seed; k.has_media = s->has_media ? 1 : 0; k.count_nodes = (p.flags & SHIM_RENDER_COUNT_NODES) ? 1 : 0;
+    k.smem = s->dev->scene.smem;
+    const bool use_smem = k.smem.total != 0 && (int)k.smem.total <= w.max_smem - 1024 && !getenv("SHIM_NO_SMEM");
+    if (!use_smem) k.smem.total = 0;
+    k.tail_threshold = 32768;
+    if (const char* e = getenv("SHIM_TAIL")) k.tail_threshold = (uint32_t)atoi(e);
 
     CU(cudaMemsetAsync(w.cnt.p, 0, CNT_WORDS * sizeof(uint32_t), st));
     CU(cudaMemsetAsync(w.accum.p, 0, w.accum.n * sizeof(float), st));
@@ -220,7 +266,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     uint64_t launches = 0;
     const bool profile = (p.flags & SHIM_RENDER_PROFILE) != 0;
     size_t prof_used = 0;
-    const size_t prof_cap = 2 * 2048;
+    const size_t prof_cap = 4 * 1024;
     if (profile && w.prof.size() < prof_cap) {
         size_t have = w.prof.size();
         w.prof.resize(prof_cap);
@@ -228,23 +274,21 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     }
     if (k.total_samples > 0 && p.max_depth > 0) {
         // iterations are enqueued in chunks; the done flag of chunk c is read back while chunk c+1 runs
-        const int chunk = 8;
+        const int chunk = 4;
         int cur = 0, pending = -1;
         bool done = false;
         for (int c = 0; !done; ++c) {
             for (int it = 0; it < chunk; ++it) {
-                wf_begin<<<1, 32, 0, st>>>(k, cur);
-                wf_generate<<<w.grid_generate, 256, 0, st>>>(k, cur);
-                const bool rec = profile && prof_used + 2 <= prof_cap;
+                const bool rec = profile && prof_used + 4 <= prof_cap;
                 if (rec) CU(cudaEventRecord(w.prof[prof_used], st));
-                wf_extend<<<w.grid_extend, 256, 0, st>>>(k, cur);
-                if (rec) { CU(cudaEventRecord(w.prof[prof_used + 1], st)); prof_used += 2; }
-                wf_shade<MAT_LAMBERTIAN><<<w.grid_shade, 256, 0, st>>>(k, cur);
-                wf_shade<MAT_METAL><<<w.grid_shade, 256, 0, st>>>(k, cur);
-                wf_shade<MAT_DIELECTRIC><<<w.grid_shade, 256, 0, st>>>(k, cur);
-                wf_shade<MAT_DIFFUSE_LIGHT><<<w.grid_shade, 256, 0, st>>>(k, cur);
-                wf_shade<MAT_ISOTROPIC><<<w.grid_shade, 256, 0, st>>>(k, cur);
-                launches += 8;
+                wf_generate<<<w.grid_generate, 256, 0, st>>>(k, cur);
+                if (rec) CU(cudaEventRecord(w.prof[prof_used + 1], st));
+                launch_extend(k, cur, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
+                if (rec) CU(cudaEventRecord(w.prof[prof_used + 2], st));
+                wf_shade<<<w.grid_shade, 256, 0, st>>>(k, cur);
+                if (k.tail_threshold) wf_tail<<<w.grid_tail, 128, 0, st>>>(k, cur);
+                if (rec) { CU(cudaEventRecord(w.prof[prof_used + 3], st)); prof_used += 4; }
+                launches += k.tail_threshold ? 4 : 3;
                 cur = 1 - cur;
             }
             int slot = c & 1;
@@ -279,11 +323,17 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         stats->device_ms = ms;
         // per-launch durations of wf_extend while it had work: launches past the done flag are skipped
         uint64_t it_done = stats->iterations;
-        for (size_t i = 0; i + 1 < prof_used && i / 2 < it_done; i += 2) {
-            float e = 0;
-            CU(cudaEventElapsedTime(&e, w.prof[i], w.prof[i + 1]));
+        const bool trace = getenv("SHIM_TRACE") != nullptr;
+        for (size_t i = 0; i + 3 < prof_used && i / 4 < it_done; i += 4) {
+            float g = 0, e = 0, sh = 0;
+            CU(cudaEventElapsedTime(&g, w.prof[i], w.prof[i + 1]));
+            CU(cudaEventElapsedTime(&e, w.prof[i + 1], w.prof[i + 2]));
+            CU(cudaEventElapsedTime(&sh, w.prof[i + 2], w.prof[i + 3]));
+            stats->generate_ms += g;
             stats->extend_ms += e;
+            stats->shade_ms += sh;
             stats->extend_launches += 1;
+            if (trace) fprintf(stderr, "shim-trace iter %3zu generate %.4f extend %.4f shade %.4f ms\n", i / 4, g, e, sh);
         }
     }
     return SHIM_OK;

@@ -170,6 +170,11 @@ SHIM_API int shim_constant_medium(shim_scene* s, int boundary, float density, in
     HostHittable c; c.kind = H_MEDIUM; c.child = boundary; c.phase_mat = push_material(s, m); c.neg_inv_density = -1.0f / density;
     return s->sb.add_hittable(c);
 }
+SHIM_API int shim_scene_set_option(shim_scene* s, int option, int value) {
+    MUTABLE(s);
+    if (option == SHIM_OPT_DEVICE_BVH) { s->sb.device_reference_topology = value == SHIM_DEVICE_BVH_REFERENCE; return SHIM_OK; }
+    return set_err(SHIM_ERR_INVALID, "shim_scene_set_option: unknown option");
+}
 SHIM_API int shim_world_add(shim_scene* s, int h) {
     MUTABLE(s);
     if (!s->sb.ok_hit(h)) return set_err(SHIM_ERR_INVALID, "shim_world_add: bad hittable id");

@@ -123,9 +123,9 @@ SHIM_HD Ray camera_sample(const CameraPod& c, int x, int y, int width, int heigh
 
 // ---------------------------------------------------------------------------- object-space ray
 struct RayCtx {
-    Ray r;            // ray as the shape sees it (after Translate / RotateY, instance.rs)
-    f3 inv_d;
-    double ox, oy, oz, dx, dy, dz, a;  // f64 copy for Sphere::hit
+    Ray r;      // ray as the shape sees it (after Translate / RotateY, instance.rs)
+    f3 inv_d;   // 1/d with |d| clamped away from 0 so that the products below stay finite
+    f3 o_inv;   // -o * inv_d: a slab plane distance is one fma(plane, inv_d, o_inv)
 };
 SHIM_HD f3 rot_y(f3 v, float s, float c) { return mk3(c * v.x - s * v.z, v.y, s * v.x + c * v.z); }       // instance.rs:104-110
 SHIM_HD f3 rot_y_back(f3 v, float s, float c) { return mk3(c * v.x + s * v.z, v.y, -s * v.x + c * v.z); } // instance.rs:125-134
@@ -135,32 +135,44 @@ SHIM_HD Ray object_ray(const DevObject& ob, const Ray& w) {
     if (ob.flags & OBJ_ROTATE) { r.o = rot_y(r.o, ob.sin_t, ob.cos_t); r.d = rot_y(r.d, ob.sin_t, ob.cos_t); }
     return r;
 }
+SHIM_HD float safe_rcp(float d) {
+    // a zero component would make fma(plane, inf, -o*inf) NaN on BOTH planes of a slab the origin lies in
+    // (and wrongly cull it); 1e-30 keeps every product finite and the interval (-huge, +huge) or empty
+    float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
+    return 1.0f / a;
+}
 SHIM_HD void make_ctx(RayCtx& c, const Ray& r) {
     c.r = r;
-    c.inv_d = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-    c.ox = (double)r.o.x; c.oy = (double)r.o.y; c.oz = (double)r.o.z;
-    c.dx = (double)r.d.x; c.dy = (double)r.d.y; c.dz = (double)r.d.z;
-    c.a = (c.dx * c.dx) + (c.dy * c.dy) + (c.dz * c.dz);
+    c.inv_d = mk3(safe_rcp(r.d.x), safe_rcp(r.d.y), safe_rcp(r.d.z));
+    c.o_inv = mk3(-(r.o.x * c.inv_d.x), -(r.o.y * c.inv_d.y), -(r.o.z * c.inv_d.z));
 }
 
 struct TraceCounters { uint32_t nodes, prims; };
 
+// per-type table lookup with constant indices only, so a SceneView held in registers is never
+// forced into local memory by a dynamic index
+SHIM_HD const int* table_of(const int* const* t, int type) {
+    return type == PT_SPHERE ? t[0] : (type == PT_MSPHERE ? t[1] : (type == PT_RECT ? t[2] : (type == PT_TRI ? t[3] : t[4])));
+}
+
 // ---------------------------------------------------------------------------- primitives
 // geometry/sphere.rs:50-89 (f64 quadratic; accepts root == t_max)
-SHIM_HD bool hit_sphere(const double* s, const RayCtx& c, float t_min, float t_max, float& t_out) {
-    double ocx = c.ox - s[0], ocy = c.oy - s[1], ocz = c.oz - s[2];
-    double half_b = (ocx * c.dx) + (ocy * c.dy) + (ocz * c.dz);
+SHIM_HD bool hit_sphere(const double* s, const Ray& r, float t_min, float t_max, float& t_out) {
+    double dx = (double)r.d.x, dy = (double)r.d.y, dz = (double)r.d.z;
+    double ocx = (double)r.o.x - s[0], ocy = (double)r.o.y - s[1], ocz = (double)r.o.z - s[2];
+    double a = (dx * dx) + (dy * dy) + (dz * dz);
+    double half_b = (ocx * dx) + (ocy * dy) + (ocz * dz);
     double cc = ((ocx * ocx) + (ocy * ocy) + (ocz * ocz)) - s[3];
-    double disc = half_b * half_b - c.a * cc;
+    double disc = half_b * half_b - a * cc;
 #if defined(__CUDA_ARCH__)
     if (__double2hiint(disc) < 0) return false;
 #else
     if (signbit(disc)) return false;
 #endif
     double sq = sqrt(disc);
-    double root = (-half_b - sq) / c.a;
+    double root = (-half_b - sq) / a;
     if (root < (double)t_min || (double)t_max < root) {
-        root = (-half_b + sq) / c.a;
+        root = (-half_b + sq) / a;
         if (root < (double)t_min || (double)t_max < root) return false;
     }
     t_out = (float)root;
@@ -246,7 +258,7 @@ SHIM_HD bool hit_cube(const f4* q, const Ray& r, float t_min, float t_max, float
 SHIM_HD bool hit_prim(const SceneView& sv, uint32_t ref, const RayCtx& c, float t_min, float t_max, float& t, int& face) {
     uint32_t i = prim_index(ref);
     switch (prim_type(ref)) {
-    case PT_SPHERE: return hit_sphere(sv.sph + 4 * (size_t)i, c, t_min, t_max, t);
+    case PT_SPHERE: return hit_sphere(sv.sph + 4 * (size_t)i, c.r, t_min, t_max, t);
     case PT_MSPHERE: return hit_msphere(sv.msph + 3 * (size_t)i, c.r, t_min, t_max, t);
     case PT_RECT: return hit_rect(sv.rect + 2 * (size_t)i, c.r, t_min, t_max, t);
     case PT_TRI: return hit_tri(sv.tri + 3 * (size_t)i, c.r, t_min, t_max, t);
@@ -259,85 +271,103 @@ SHIM_HD bool hit_prim(const SceneView& sv, uint32_t ref, const RayCtx& c, float 
 // Result contract (bvh.rs:363-417): the brute-force closest hit over the subtree's
 // primitives, each tested as Hittable::hit(ray, t_min, t_max); among primitives with exactly
 // equal t the one latest in left-to-right leaf order wins (`left.t < right.t` else right).
-// Any visiting order satisfies it as long as ties are resolved by leaf rank.
-SHIM_HD bool slab(f3 mn, f3 mx, const RayCtx& c, float t_min, float t_max, float& t_near) {
-    float x0 = (mn.x - c.r.o.x) * c.inv_d.x, x1 = (mx.x - c.r.o.x) * c.inv_d.x;
-    float y0 = (mn.y - c.r.o.y) * c.inv_d.y, y1 = (mx.y - c.r.o.y) * c.inv_d.y;
-    float z0 = (mn.z - c.r.o.z) * c.inv_d.z, z1 = (mx.z - c.r.o.z) * c.inv_d.z;
-    // fminf/fmaxf drop NaNs (0 * inf), which only makes the test more permissive
+// Any visiting order satisfies it as long as ties are resolved by leaf rank (sv.rank[]).
+//
+// The walk is a while-while loop with a short stack: phase 1 descends inner nodes (one 64-byte
+// node = both child boxes, four 16-byte loads, two fused-multiply-add slab tests, near child
+// first) until the lane's next entry is a primitive; phase 2 tests that primitive.  Lanes of a
+// warp therefore run their primitive tests (the f64 sphere quadratic) together.
+SHIM_HD float slab_plane(float plane, float inv, float o_inv) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(plane, inv, o_inv);
+#else
+    return fmaf(plane, inv, o_inv);
+#endif
+}
+SHIM_HD bool slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const RayCtx& c, float t_min, float t_max,
+                  float& t_near) {
+    float x0 = slab_plane(mnx, c.inv_d.x, c.o_inv.x), x1 = slab_plane(mxx, c.inv_d.x, c.o_inv.x);
+    float y0 = slab_plane(mny, c.inv_d.y, c.o_inv.y), y1 = slab_plane(mxy, c.inv_d.y, c.o_inv.y);
+    float z0 = slab_plane(mnz, c.inv_d.z, c.o_inv.z), z1 = slab_plane(mxz, c.inv_d.z, c.o_inv.z);
     float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_min));
     float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
     t_near = tn;
     return !(tf < tn);  // aabb.rs:36 rejects only when t_max < t_min
 }
 
-struct BvhBest { float t; int rank; uint32_t prim; int face; int leaf; };
-
-SHIM_HD void bvh_leaf_test(const SceneView& sv, int child, int rank, int node_index, const RayCtx& c, float t_min, BvhBest& best,
-                           TraceCounters* cnt) {
-    uint32_t ref = ~(uint32_t)child;
-    float t; int face = 0;
-    if (cnt) cnt->prims++;
-    if (hit_prim(sv, ref, c, t_min, best.t, t, face)) {
-        if (t < best.t || rank > best.rank) { best.t = t; best.rank = rank; best.prim = ref; best.face = face; best.leaf = node_index; }
-    }
-}
+struct BvhBest { float t; uint32_t prim; int face; bool any; };
 
 #define SHIM_BVH_STACK 40
+#define SHIM_STACK_END 0x7fffffff
+template <bool COUNT>
 SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, float t_min, float t_max, BvhBest& best,
                          TraceCounters* cnt) {
-    best.t = t_max; best.rank = -1; best.prim = 0; best.face = 0; best.leaf = -1;
+    best.t = t_max; best.prim = 0; best.face = 0; best.any = false;
+    // Boxes are culled against the closest hit so far (the reference never does: BvhNode::hit passes the caller's
+    // t_max down unchanged, bvh.rs:385-394).  A primitive that TIES the current best often touches its own box
+    // (a cube face is its box face), and the box entry is computed by different arithmetic than the primitive's
+    // t, so the cull uses best.t widened by 2^-18 relative: ties are always tested and the tie rule decides.
+    float t_cull = t_max;
     int stack[SHIM_BVH_STACK];
     int sp = 0;
-    int node = start_node;
+    int cur = start_node;  // >= 0 inner node, < 0 ~prim_ref, SHIM_STACK_END when done
     for (;;) {
-        const DevNode& n = sv.nodes[node];
-        f4 na = n.a, nb = n.b, nc = n.c;
-        i4 nd = n.d;
-        if (cnt) cnt->nodes++;
-        float tl, tr;
-        bool hl = nd.x != CHILD_NONE && slab(mk3(na.x, na.y, na.z), mk3(na.w, nb.x, nb.y), c, t_min, best.t, tl);
-        bool hr = nd.y != CHILD_NONE && slab(mk3(nb.z, nb.w, nc.x), mk3(nc.y, nc.z, nc.w), c, t_min, best.t, tr);
-        // primitive children are tested on the spot
-        if (hl && nd.x < 0) { bvh_leaf_test(sv, nd.x, nd.w, node, c, t_min, best, cnt); hl = false; }
-        if (hr && nd.y < 0) {
-            // the left primitive may have shrunk best.t; re-check the right box cheaply
-            if (!(best.t < tr)) bvh_leaf_test(sv, nd.y, nd.w + (nd.x < 0 ? 1 : 0), node, c, t_min, best, cnt);
-            hr = false;
+        while (cur >= 0 && cur != SHIM_STACK_END) {
+            const DevNode& n = sv.nodes[cur];
+            f4 na = n.a, nb = n.b, nc = n.c;
+            i4 nd = n.d;
+            if (COUNT) cnt->nodes++;
+            float tl, tr;
+            bool hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, t_min, t_cull, tl);
+            bool hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, t_min, t_cull, tr);
+            hr = hr && nd.y != CHILD_NONE;
+            if (hl && hr) {
+                bool swap = tr < tl;
+                cur = swap ? nd.y : nd.x;
+                if (sp < SHIM_BVH_STACK) stack[sp++] = swap ? nd.x : nd.y;
+            } else if (hl) {
+                cur = nd.x;
+            } else if (hr) {
+                cur = nd.y;
+            } else {
+                cur = sp > 0 ? stack[--sp] : SHIM_STACK_END;
+            }
         }
-        if (hl && hr) {
-            int nearc = nd.x, farc = nd.y;
-            if (tr < tl) { nearc = nd.y; farc = nd.x; }
-            if (sp < SHIM_BVH_STACK) stack[sp++] = farc;
-            node = nearc;
-        } else if (hl) {
-            node = nd.x;
-        } else if (hr) {
-            node = nd.y;
-        } else {
-            if (sp == 0) break;
-            node = stack[--sp];
+        if (cur == SHIM_STACK_END) break;
+        {
+            uint32_t ref = ~(uint32_t)cur;
+            float t; int face = 0;
+            if (COUNT) cnt->prims++;
+            if (hit_prim(sv, ref, c, t_min, best.t, t, face)) {
+                // accepted t <= best.t; an exact tie goes to the later leaf (bvh.rs:409-415)
+                bool take = !best.any || t < best.t ||
+                            table_of(sv.rank, prim_type(ref))[prim_index(ref)] > table_of(sv.rank, prim_type(best.prim))[prim_index(best.prim)];
+                if (take) { best.t = t; best.prim = ref; best.face = face; best.any = true; t_cull = t + fabsf(t) * 3.8146973e-06f; }
+            }
+            cur = sp > 0 ? stack[--sp] : SHIM_STACK_END;
         }
     }
-    return best.rank >= 0;
+    return best.any;
 }
 
 // shape of one top-level object against its object-space ray
+template <bool COUNT>
 SHIM_HD bool shape_hit(const SceneView& sv, const DevObject& ob, const RayCtx& c, float t_min, float t_max, float& t, uint32_t& prim,
-                       int& face, int& leaf, TraceCounters* cnt) {
+                       int& face, TraceCounters* cnt) {
     if (ob.kind == OBJ_PRIM) {
-        face = 0; leaf = -1;
-        if (cnt) cnt->prims++;
+        face = 0;
+        if (COUNT) cnt->prims++;
         if (hit_prim(sv, (uint32_t)ob.ref, c, t_min, t_max, t, face)) { prim = (uint32_t)ob.ref; return true; }
         return false;
     }
     BvhBest best;
-    if (bvh_closest(sv, ob.ref, c, t_min, t_max, best, cnt)) { t = best.t; prim = best.prim; face = best.face; leaf = best.leaf; return true; }
+    if (bvh_closest<COUNT>(sv, ob.ref, c, t_min, t_max, best, cnt)) { t = best.t; prim = best.prim; face = best.face; return true; }
     return false;
 }
 
 // HittableList::hit over the flattened world (hittable.rs:100-118), with ConstantMedium::hit
 // (hittable.rs:177-233) for medium objects.  `rng` must be keyed to STAGE_INTERSECT.
+template <bool COUNT>
 SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float t_max, Rng& rng, TraceCounters* cnt) {
     Hit h; h.t = t_max; h.obj = -1; h.prim = 0; h.face = 0;
     float closest = t_max;
@@ -345,11 +375,11 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
         const DevObject& ob = sv.objects[oi];
         RayCtx c;
         make_ctx(c, object_ray(ob, ray));
-        float t; uint32_t prim; int face, leaf;
+        float t; uint32_t prim; int face;
         if (ob.flags & OBJ_MEDIUM) {
             float t1, t2;
-            if (!shape_hit(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, leaf, cnt)) continue;
-            if (!shape_hit(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, leaf, cnt)) continue;
+            if (!shape_hit<COUNT>(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, cnt)) continue;
+            if (!shape_hit<COUNT>(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, cnt)) continue;
             if (t1 < t_min) t1 = t_min;
             if (t2 > closest) t2 = closest;
             if (t1 >= t2) continue;
@@ -361,7 +391,7 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
             t = t1 + hit_distance / ray_length;
             closest = t;
             h.t = t; h.obj = oi; h.prim = 0; h.face = 0;
-        } else if (shape_hit(sv, ob, c, t_min, closest, t, prim, face, leaf, cnt)) {
+        } else if (shape_hit<COUNT>(sv, ob, c, t_min, closest, t, prim, face, cnt)) {
             closest = t;
             h.t = t; h.obj = oi; h.prim = prim; h.face = face;
         }
@@ -387,7 +417,7 @@ SHIM_HD int hit_handle(const SceneView& sv, const Hit& h) {
     if (h.obj < 0) return -1;
     const DevObject& ob = sv.objects[h.obj];
     if (ob.flags & OBJ_MEDIUM) return ob.handle;
-    return sv.handle[prim_type(h.prim)][prim_index(h.prim)];
+    return table_of(sv.handle, prim_type(h.prim))[prim_index(h.prim)];
 }
 
 // ---------------------------------------------------------------------------- hit record

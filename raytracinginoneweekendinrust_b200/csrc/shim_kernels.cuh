@@ -1,15 +1,22 @@
 // shim_kernels.cuh — sm_100a wavefront kernels.
 //
 // One iteration of the wavefront (replaces the per-tile loop of renderer.rs:63-85 and the
-// recursion of ray.rs:32-62):
+// recursion of ray.rs:32-62) is three launches:
 //
-//   wf_begin     1 thread: tops the current ray queue up with new camera samples
-//   wf_generate  camera rays for those samples (renderer.rs:141-143, camera.rs:96-106)
-//   wf_extend    closest hit for every queued ray (hittable.rs:100-118); misses add the
-//                background on the spot; hits are binned into per-material queues with one
-//                atomic per warp and material
-//   wf_shade<M>  one kernel per material kind: rebuild the HitRecord, emit, scatter, and
-//                append the continuing ray to the next queue (warp-ballot compaction)
+//   wf_generate  tops the current ray queue up with camera rays for new samples
+//                (renderer.rs:141-143, camera.rs:96-106); the last block to finish advances the
+//                device-side counters for the iteration
+//   wf_extend    closest hit for every queued ray (hittable.rs:100-118).  The BVH nodes and
+//                primitive arrays are staged into shared memory by TMA bulk copies
+//                (cp.async.bulk + mbarrier) when they fit, so the walk's 16-byte node fetches
+//                are LDS; misses add the background on the spot; hits are binned into
+//                per-material queues with one atomic per warp and material
+//   wf_shade     one launch covering the five material queues (each 256-ray chunk of a queue is
+//                shaded by code specialised for that material): rebuild the HitRecord, emit,
+//                scatter, and append the continuing ray to the next queue (warp-ballot compaction)
+//   wf_tail      once no samples are left to start and only a few thousand paths are alive, one
+//                launch finishes them (extend + shade in a loop per thread) instead of ~40
+//                near-empty iterations
 //
 // Ray queues are SoA float4 streams in HBM, double buffered; all counts live on the device,
 // the host only polls a done flag every few iterations.
@@ -19,10 +26,17 @@
 
 namespace shim {
 
-enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..6 */, CNT_GEN_BASE = 8, CNT_GEN_COUNT = 9, CNT_DONE = 10, CNT_ITER = 11,
+enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..6 */, CNT_TICKET = 8, CNT_DONE = 10, CNT_ITER = 11,
        CNT_U64_BASE = 12 /* u64 slots from here, as pairs */ };
-enum { C64_NEXT_SAMPLE = 0, C64_GEN_FIRST = 1, C64_RAYS = 2, C64_NODES = 3, C64_PRIMS = 4, C64_COUNT = 5 };
+enum { C64_NEXT_SAMPLE = 0, C64_RAYS = 1, C64_NODES = 2, C64_PRIMS = 3, C64_COUNT = 4 };
 enum { CNT_WORDS = CNT_U64_BASE + 2 * C64_COUNT };
+
+// shared-memory image of the scene arrays wf_extend walks (byte offsets, all multiples of 16)
+struct SmemLayout {
+    uint32_t off_nodes, off_sph, off_msph, off_rect, off_tri, off_cube, off_objects;
+    uint32_t bytes_nodes, bytes_sph, bytes_msph, bytes_rect, bytes_tri, bytes_cube, bytes_objects;
+    uint32_t total;  // 0 = scene does not fit: walk it in global memory (L2)
+};
 
 struct WfParams {
     SceneView sv;
@@ -40,10 +54,12 @@ struct WfParams {
     uint32_t npix;            // pixels rendered by this call (tile shard)
     uint64_t total_samples;   // npix * sample_count
     uint32_t pool;
+    uint32_t tail_threshold;
     int width, height, max_depth, sample_begin;
     float bg[3];
     uint64_t seed;
     int has_media, count_nodes;
+    SmemLayout smem;
 };
 
 __device__ __forceinline__ unsigned long long* cnt64(uint32_t* cnt, int slot) {
@@ -62,31 +78,44 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred) {
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
 
-__global__ void wf_begin(WfParams p, int cur) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint32_t* c = p.cnt;
-    uint32_t n_cur = c[cur];
-    unsigned long long next = *cnt64(c, C64_NEXT_SAMPLE);
-    unsigned long long remaining = p.total_samples - next;
-    unsigned long long room = (unsigned long long)(p.pool - n_cur);
-    uint32_t n_new = (uint32_t)(remaining < room ? remaining : room);
-    c[CNT_GEN_BASE] = n_cur;
-    c[CNT_GEN_COUNT] = n_new;
-    *cnt64(c, C64_GEN_FIRST) = next;
-    *cnt64(c, C64_NEXT_SAMPLE) = next + n_new;
-    c[cur] = n_cur + n_new;
-    c[1 - cur] = 0;
-#pragma unroll
-    for (int k = 0; k < MAT_KINDS; ++k) c[CNT_MQ + k] = 0;
-    *cnt64(c, C64_RAYS) += (unsigned long long)(n_cur + n_new);
-    c[CNT_DONE] = (n_cur + n_new == 0) ? 1u : 0u;
-    c[CNT_ITER] += (n_cur + n_new == 0) ? 0u : 1u;
+// ---------------------------------------------------------------------------- TMA bulk copy helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
+// ---------------------------------------------------------------------------- generate
+// All blocks read the pre-iteration counters, write their camera rays, and the last block to
+// finish (ticket) publishes the counters the rest of the iteration uses.
 __global__ void __launch_bounds__(256) wf_generate(WfParams p, int cur) {
-    const uint32_t n = p.cnt[CNT_GEN_COUNT];
-    const uint32_t base = p.cnt[CNT_GEN_BASE];
-    const unsigned long long first = *cnt64(p.cnt, C64_GEN_FIRST);
+    uint32_t* c = p.cnt;
+    const uint32_t n_cur = c[cur];
+    const unsigned long long first = *cnt64(c, C64_NEXT_SAMPLE);
+    const unsigned long long remaining = p.total_samples - first;
+    const unsigned long long room = (unsigned long long)(p.pool - n_cur);
+    const uint32_t n = (uint32_t)(remaining < room ? remaining : room);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         unsigned long long g = first + j;
         uint32_t s = (uint32_t)(g / p.npix);
@@ -98,7 +127,7 @@ __global__ void __launch_bounds__(256) wf_generate(WfParams p, int cur) {
         rng_init(rng, pixel, sample, p.seed);
         rng_key(rng, 0, STAGE_CAMERA);
         Ray r = camera_sample(p.cam, x, y, p.width, p.height, rng);
-        uint32_t slot = base + j;
+        uint32_t slot = n_cur + j;
         f4 o; o.x = r.o.x; o.y = r.o.y; o.z = r.o.z; o.w = r.time;
         f4 d; d.x = r.d.x; d.y = r.d.y; d.z = r.d.z; d.w = i2f(0);
         f4 t; t.x = 1.0f; t.y = 1.0f; t.z = 1.0f; t.w = i2f((int)pixel);
@@ -107,10 +136,28 @@ __global__ void __launch_bounds__(256) wf_generate(WfParams p, int cur) {
         p.thr[cur][slot] = t;
         p.samp[cur][slot] = sample;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t ticket = atomicAdd(c + CNT_TICKET, 1u);
+        if (ticket == gridDim.x - 1) {  // every block has read the old counters: publish the new ones
+            c[CNT_TICKET] = 0;
+            *cnt64(c, C64_NEXT_SAMPLE) = first + n;
+            c[cur] = n_cur + n;
+            c[1 - cur] = 0;
+#pragma unroll
+            for (int k = 0; k < MAT_KINDS; ++k) c[CNT_MQ + k] = 0;
+            *cnt64(c, C64_RAYS) += (unsigned long long)(n_cur + n);
+            c[CNT_DONE] = (n_cur + n == 0) ? 1u : 0u;
+            c[CNT_ITER] += (n_cur + n == 0) ? 0u : 1u;
+            __threadfence();
+        }
+    }
 }
 
-__global__ void __launch_bounds__(256) wf_extend(WfParams p, int cur) {
-    const uint32_t n = p.cnt[cur];
+// ---------------------------------------------------------------------------- extend
+template <bool COUNT, bool MEDIA>
+__device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& sv, int cur, uint32_t n) {
     const uint32_t n_round = (n + 31u) & ~31u;
     uint32_t nodes = 0, prims = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -120,14 +167,14 @@ __global__ void __launch_bounds__(256) wf_extend(WfParams p, int cur) {
             f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i];
             Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
             Rng rng;
-            if (p.has_media) {
+            if (MEDIA) {
                 rng_init(rng, (uint32_t)f2i(p.thr[cur][i].w), p.samp[cur][i], p.seed);
                 rng_key(rng, (uint32_t)f2i(d.w), STAGE_INTERSECT);
             } else {
                 rng_init(rng, 0, 0, 0);
             }
             TraceCounters tc; tc.nodes = 0; tc.prims = 0;
-            Hit h = closest_hit(p.sv, r, 0.001f, SHIM_INF, rng, p.count_nodes ? &tc : nullptr);
+            Hit h = closest_hit<COUNT>(sv, r, 0.001f, SHIM_INF, rng, &tc);
             nodes += tc.nodes; prims += tc.prims;
             if (h.obj < 0) {  // ray.rs:60: miss returns the background
                 if (p.bg[0] != 0.0f || p.bg[1] != 0.0f || p.bg[2] != 0.0f) {
@@ -138,8 +185,8 @@ __global__ void __launch_bounds__(256) wf_extend(WfParams p, int cur) {
                     atomicAdd(a + 2, t.z * p.bg[2]);
                 }
             } else {
-                int mat = hit_material(p.sv, h);
-                kind = mat_kind(p.sv, mat);
+                int mat = hit_material(sv, h);
+                kind = mat_kind(sv, mat);
                 f4 hv; hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat);
                 p.hit[i] = hv;
             }
@@ -150,62 +197,174 @@ __global__ void __launch_bounds__(256) wf_extend(WfParams p, int cur) {
             if (kind == k) p.mq[k][pos] = i;
         }
     }
-    if (p.count_nodes) {
+    if (COUNT) {
         atomicAdd(cnt64(p.cnt, C64_NODES), (unsigned long long)nodes);
         atomicAdd(cnt64(p.cnt, C64_PRIMS), (unsigned long long)prims);
     }
 }
 
+#ifndef SHIM_EXTEND_THREADS
+#define SHIM_EXTEND_THREADS 768
+#endif
+template <bool SMEM, bool COUNT, bool MEDIA>
+__global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend(WfParams p, int cur) {
+    const uint32_t n = p.cnt[cur];
+    if (blockIdx.x * blockDim.x >= n) return;  // nothing for this block: do not even stage the scene
+    SceneView sv = p.sv;
+    if (SMEM) {
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t bar;
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const SmemLayout& L = p.smem;
+            mbar_expect_tx(&bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects);
+            if (L.bytes_nodes) bulk_g2s(smem + L.off_nodes, p.sv.nodes, L.bytes_nodes, &bar);
+            if (L.bytes_sph) bulk_g2s(smem + L.off_sph, p.sv.sph, L.bytes_sph, &bar);
+            if (L.bytes_msph) bulk_g2s(smem + L.off_msph, p.sv.msph, L.bytes_msph, &bar);
+            if (L.bytes_rect) bulk_g2s(smem + L.off_rect, p.sv.rect, L.bytes_rect, &bar);
+            if (L.bytes_tri) bulk_g2s(smem + L.off_tri, p.sv.tri, L.bytes_tri, &bar);
+            if (L.bytes_cube) bulk_g2s(smem + L.off_cube, p.sv.cube, L.bytes_cube, &bar);
+            if (L.bytes_objects) bulk_g2s(smem + L.off_objects, p.sv.objects, L.bytes_objects, &bar);
+        }
+        sv.nodes = reinterpret_cast<const DevNode*>(smem + p.smem.off_nodes);
+        sv.sph = reinterpret_cast<const double*>(smem + p.smem.off_sph);
+        sv.msph = reinterpret_cast<const f4*>(smem + p.smem.off_msph);
+        sv.rect = reinterpret_cast<const f4*>(smem + p.smem.off_rect);
+        sv.tri = reinterpret_cast<const f4*>(smem + p.smem.off_tri);
+        sv.cube = reinterpret_cast<const f4*>(smem + p.smem.off_cube);
+        sv.objects = reinterpret_cast<const DevObject*>(smem + p.smem.off_objects);
+        mbar_wait(&bar, 0);
+    }
+    extend_rays<COUNT, MEDIA>(p, sv, cur, n);
+}
+
+// ---------------------------------------------------------------------------- shade
+struct ShadeOut { bool cont; Ray ray; f3 thr; };
+
+// ray.rs:44-58 for one hit of material kind KIND; adds emission to the framebuffer
 template <int KIND>
-__global__ void __launch_bounds__(256) wf_shade(WfParams p, int cur) {
+__device__ __forceinline__ void shade_one(const WfParams& p, const SceneView& sv, const Ray& r, const Hit& h, int mat, f3 thr, int bounce,
+                                          uint32_t pixel, uint32_t sample, ShadeOut& out) {
+    HitRec rec;
+    reconstruct_hit(sv, r, h, mat_needs_uv(sv, mat), rec);
+    out.cont = false;
+    if (KIND == MAT_DIFFUSE_LIGHT) {  // ray.rs:46-48, 57: emitted, no scatter
+        f3 e = mat_emit(sv, mat, rec);
+        float* a = p.accum + 3 * (size_t)pixel;
+        atomicAdd(a + 0, thr.x * e.x);
+        atomicAdd(a + 1, thr.y * e.y);
+        atomicAdd(a + 2, thr.z * e.z);
+    } else {
+        Rng rng;
+        rng_init(rng, pixel, sample, p.seed);
+        rng_key(rng, (uint32_t)bounce, STAGE_SCATTER);
+        f3 att;
+        if (mat_scatter(sv, KIND, mat, r, rec, rng, att, out.ray)) {
+            out.thr = thr * att;
+            out.cont = bounce + 1 < p.max_depth;  // ray.rs:39-42: depth exhausted -> black
+        }
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void shade_chunk(const WfParams& p, int cur, uint32_t j, uint32_t n) {
     const int nxt = 1 - cur;
-    const uint32_t n = p.cnt[CNT_MQ + KIND];
-    const uint32_t n_round = (n + 31u) & ~31u;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
-        bool cont = false;
-        Ray out; out.o = mk3(0, 0, 0); out.d = mk3(0, 0, 0); out.time = 0;
-        f3 thr = mk3(0, 0, 0);
-        int bounce = 0, pixel = 0; uint32_t sample = 0;
-        if (j < n) {
-            uint32_t i = p.mq[KIND][j];
-            f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i], t = p.thr[cur][i], hv = p.hit[i];
-            sample = p.samp[cur][i];
-            Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
-            bounce = f2i(d.w); pixel = f2i(t.w);
-            thr = mk3(t.x, t.y, t.z);
-            Hit h; h.t = hv.x; h.obj = f2i(hv.y) & 0xffff; h.face = f2i(hv.y) >> 16; h.prim = (uint32_t)f2i(hv.z);
-            int mat = f2i(hv.w);
-            HitRec rec;
-            reconstruct_hit(p.sv, r, h, mat_needs_uv(p.sv, mat), rec);
-            if (KIND == MAT_DIFFUSE_LIGHT) {  // ray.rs:46-48, 57: emitted, no scatter
-                f3 e = mat_emit(p.sv, mat, rec);
-                float* a = p.accum + 3 * (size_t)(uint32_t)pixel;
-                atomicAdd(a + 0, thr.x * e.x);
-                atomicAdd(a + 1, thr.y * e.y);
-                atomicAdd(a + 2, thr.z * e.z);
-            } else {
-                Rng rng;
-                rng_init(rng, (uint32_t)pixel, sample, p.seed);
-                rng_key(rng, (uint32_t)bounce, STAGE_SCATTER);
-                f3 att;
-                if (mat_scatter(p.sv, KIND, mat, r, rec, rng, att, out)) {
-                    thr = thr * att;
-                    cont = bounce + 1 < p.max_depth;  // ray.rs:39-42: depth exhausted -> black
-                }
-            }
+    ShadeOut so;
+    so.cont = false; so.ray.o = mk3(0, 0, 0); so.ray.d = mk3(0, 0, 0); so.ray.time = 0; so.thr = mk3(0, 0, 0);
+    int bounce = 0; uint32_t pixel = 0, sample = 0;
+    if (j < n) {
+        uint32_t i = p.mq[KIND][j];
+        f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i], t = p.thr[cur][i], hv = p.hit[i];
+        sample = p.samp[cur][i];
+        Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
+        bounce = f2i(d.w); pixel = (uint32_t)f2i(t.w);
+        Hit h; h.t = hv.x; h.obj = f2i(hv.y) & 0xffff; h.face = f2i(hv.y) >> 16; h.prim = (uint32_t)f2i(hv.z);
+        shade_one<KIND>(p, p.sv, r, h, f2i(hv.w), mk3(t.x, t.y, t.z), bounce, pixel, sample, so);
+    }
+    if (KIND != MAT_DIFFUSE_LIGHT) {
+        uint32_t pos = warp_append(p.cnt + nxt, so.cont);
+        if (so.cont) {
+            f4 o; o.x = so.ray.o.x; o.y = so.ray.o.y; o.z = so.ray.o.z; o.w = so.ray.time;
+            f4 d; d.x = so.ray.d.x; d.y = so.ray.d.y; d.z = so.ray.d.z; d.w = i2f(bounce + 1);
+            f4 t; t.x = so.thr.x; t.y = so.thr.y; t.z = so.thr.z; t.w = i2f((int)pixel);
+            p.ray_o[nxt][pos] = o;
+            p.ray_d[nxt][pos] = d;
+            p.thr[nxt][pos] = t;
+            p.samp[nxt][pos] = sample;
         }
-        if (KIND != MAT_DIFFUSE_LIGHT) {
-            uint32_t pos = warp_append(p.cnt + nxt, cont);
-            if (cont) {
-                f4 o; o.x = out.o.x; o.y = out.o.y; o.z = out.o.z; o.w = out.time;
-                f4 d; d.x = out.d.x; d.y = out.d.y; d.z = out.d.z; d.w = i2f(bounce + 1);
-                f4 t; t.x = thr.x; t.y = thr.y; t.z = thr.z; t.w = i2f(pixel);
-                p.ray_o[nxt][pos] = o;
-                p.ray_d[nxt][pos] = d;
-                p.thr[nxt][pos] = t;
-                p.samp[nxt][pos] = sample;
+    }
+}
+
+// One launch for all material queues: the queues are cut into 256-ray chunks, chunks are dealt
+// round-robin to the persistent blocks, and each chunk runs the code specialised for its material.
+__global__ void __launch_bounds__(256) wf_shade(WfParams p, int cur) {
+    uint32_t n[MAT_KINDS], first[MAT_KINDS + 1];
+    first[0] = 0;
+#pragma unroll
+    for (int k = 0; k < MAT_KINDS; ++k) {
+        n[k] = p.cnt[CNT_MQ + k];
+        first[k + 1] = first[k] + (n[k] + 255u) / 256u;
+    }
+    for (uint32_t w = blockIdx.x; w < first[MAT_KINDS]; w += gridDim.x) {
+        if (w < first[1]) shade_chunk<MAT_LAMBERTIAN>(p, cur, (w - first[0]) * 256u + threadIdx.x, n[0]);
+        else if (w < first[2]) shade_chunk<MAT_METAL>(p, cur, (w - first[1]) * 256u + threadIdx.x, n[1]);
+        else if (w < first[3]) shade_chunk<MAT_DIELECTRIC>(p, cur, (w - first[2]) * 256u + threadIdx.x, n[2]);
+        else if (w < first[4]) shade_chunk<MAT_DIFFUSE_LIGHT>(p, cur, (w - first[3]) * 256u + threadIdx.x, n[3]);
+        else shade_chunk<MAT_ISOTROPIC>(p, cur, (w - first[4]) * 256u + threadIdx.x, n[4]);
+    }
+}
+
+// ---------------------------------------------------------------------------- tail
+// Runs after wf_shade.  When every sample has been started and at most tail_threshold paths are
+// alive, each thread takes one of them and follows it to its end; the queue is then empty.
+__global__ void __launch_bounds__(128) wf_tail(WfParams p, int cur) {
+    const int nxt = 1 - cur;
+    const uint32_t n = p.cnt[nxt];
+    if (n == 0 || n > p.tail_threshold || *cnt64(p.cnt, C64_NEXT_SAMPLE) < p.total_samples) return;
+    uint32_t traced = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        f4 o = p.ray_o[nxt][i], d = p.ray_d[nxt][i], t = p.thr[nxt][i];
+        uint32_t sample = p.samp[nxt][i], pixel = (uint32_t)f2i(t.w);
+        Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
+        f3 thr = mk3(t.x, t.y, t.z);
+        for (int bounce = f2i(d.w); bounce < p.max_depth; ++bounce) {
+            Rng rng;
+            rng_init(rng, pixel, sample, p.seed);
+            rng_key(rng, (uint32_t)bounce, STAGE_INTERSECT);
+            ++traced;
+            Hit h = closest_hit<false>(p.sv, r, 0.001f, SHIM_INF, rng, nullptr);
+            if (h.obj < 0) {
+                float* a = p.accum + 3 * (size_t)pixel;
+                atomicAdd(a + 0, thr.x * p.bg[0]);
+                atomicAdd(a + 1, thr.y * p.bg[1]);
+                atomicAdd(a + 2, thr.z * p.bg[2]);
+                break;
             }
+            int mat = hit_material(p.sv, h);
+            ShadeOut so;
+            so.cont = false;
+            switch (mat_kind(p.sv, mat)) {
+            case MAT_LAMBERTIAN: shade_one<MAT_LAMBERTIAN>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            case MAT_METAL: shade_one<MAT_METAL>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            case MAT_DIELECTRIC: shade_one<MAT_DIELECTRIC>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            case MAT_DIFFUSE_LIGHT: shade_one<MAT_DIFFUSE_LIGHT>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            default: shade_one<MAT_ISOTROPIC>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            }
+            if (!so.cont) break;
+            r = so.ray;
+            thr = so.thr;
         }
+    }
+    // queue `nxt` has not been counted yet (wf_generate counts a queue when its iteration starts)
+    unsigned long long extra = traced;
+    for (int off = 16; off > 0; off >>= 1) extra += __shfl_down_sync(0xffffffffu, extra, off);
+    if ((threadIdx.x & 31) == 0 && extra) atomicAdd(cnt64(p.cnt, C64_RAYS), extra);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t ticket = atomicAdd(p.cnt + CNT_TICKET, 1u);
+        if (ticket == gridDim.x - 1) { p.cnt[CNT_TICKET] = 0; p.cnt[nxt] = 0; __threadfence(); }
     }
 }
 
@@ -226,7 +385,7 @@ __global__ void __launch_bounds__(256) trace_closest_kernel(SceneView sv, const 
         rng_init(rng, (uint32_t)i, 0, seed);
         rng_key(rng, 0, STAGE_INTERSECT);
         TraceCounters tc; tc.nodes = 0; tc.prims = 0;
-        Hit h = closest_hit(sv, r, t_min, t_max, rng, counters ? &tc : nullptr);
+        Hit h = counters ? closest_hit<true>(sv, r, t_min, t_max, rng, &tc) : closest_hit<false>(sv, r, t_min, t_max, rng, nullptr);
         nodes += tc.nodes; prims += tc.prims;
         prim_id[i] = hit_handle(sv, h);
         t_out[i] = h.obj < 0 ? SHIM_INF : h.t;

@@ -164,6 +164,132 @@ int SceneBuilder::bvh_from_nodes(int n, const int32_t* left, const int32_t* righ
     return add_hittable(bvh);
 }
 
+// ---------------------------------------------------------------------------- device tree (binned SAH)
+// The closest hit does not depend on the tree, so the tree the kernels walk is
+// rebuilt from the BVH's primitive list with a binned surface-area heuristic instead of bvh.rs's
+// random-axis median split (19 -> ~8 node visits per ray on the Book-1 scene).  The reference
+// topology stays in HostHittable::nodes (shim_bvh_nodes) and can be selected for the device too.
+namespace {
+struct SahBuilder {
+    const std::vector<int>& prims;            // hittable ids
+    const std::vector<Box>& boxes;            // box of prims[i]
+    std::vector<HostBvhNode>& out;
+    std::vector<int> idx;
+    static float area(const Box& b) {
+        float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
+        if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0.0f;
+        return 2.0f * (dx * dy + dy * dz + dz * dx);
+    }
+    static Box empty() { Box b; for (int k = 0; k < 3; ++k) { b.mn[k] = INFINITY; b.mx[k] = -INFINITY; } return b; }
+    static int ceil_log2(size_t n) { int l = 0; while (((size_t)1 << l) < n) ++l; return l; }
+
+    // returns a child reference: >= 0 node index, < 0 ~hittable id
+    int build(size_t lo, size_t hi, int depth, Box& box_out) {
+        size_t n = hi - lo;
+        if (n == 1) { box_out = boxes[idx[lo]]; return ~prims[idx[lo]]; }
+        Box bounds = empty(), cb = empty();
+        for (size_t i = lo; i < hi; ++i) {
+            const Box& b = boxes[idx[i]];
+            bounds = box_union(bounds, b);
+            for (int k = 0; k < 3; ++k) {
+                float c = 0.5f * (b.mn[k] + b.mx[k]);
+                cb.mn[k] = std::fmin(cb.mn[k], c); cb.mx[k] = std::fmax(cb.mx[k], c);
+            }
+        }
+        size_t mid = lo + n / 2;
+        bool median = depth + ceil_log2(n) >= SHIM_MAX_BVH_HEIGHT - 2;  // keep the height inside the traversal stack
+        int best_axis = -1; int best_bin = -1;
+        const int NB = 32;
+        if (!median && n > 2) {
+            float best_cost = INFINITY;
+            for (int axis = 0; axis < 3; ++axis) {
+                float ext = cb.mx[axis] - cb.mn[axis];
+                if (!(ext > 0.0f)) continue;
+                Box bb[NB]; int cnt[NB];
+                for (int b = 0; b < NB; ++b) { bb[b] = empty(); cnt[b] = 0; }
+                float scale = (float)NB / ext;
+                for (size_t i = lo; i < hi; ++i) {
+                    const Box& bx = boxes[idx[i]];
+                    int b = (int)((0.5f * (bx.mn[axis] + bx.mx[axis]) - cb.mn[axis]) * scale);
+                    b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                    bb[b] = box_union(bb[b], bx); cnt[b]++;
+                }
+                float right_area[NB]; int right_cnt[NB];
+                Box acc = empty(); int c = 0;
+                for (int b = NB - 1; b > 0; --b) { acc = box_union(acc, bb[b]); c += cnt[b]; right_area[b] = area(acc); right_cnt[b] = c; }
+                acc = empty(); c = 0;
+                for (int b = 0; b < NB - 1; ++b) {
+                    acc = box_union(acc, bb[b]); c += cnt[b];
+                    if (c == 0 || right_cnt[b + 1] == 0) continue;
+                    float cost = area(acc) * (float)c + right_area[b + 1] * (float)right_cnt[b + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+                }
+            }
+        }
+        if (best_axis >= 0) {
+            float ext = cb.mx[best_axis] - cb.mn[best_axis];
+            float scale = (float)NB / ext;
+            auto it = std::partition(idx.begin() + lo, idx.begin() + hi, [&](int i) {
+                const Box& bx = boxes[i];
+                int b = (int)((0.5f * (bx.mn[best_axis] + bx.mx[best_axis]) - cb.mn[best_axis]) * scale);
+                b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                return b <= best_bin;
+            });
+            mid = (size_t)(it - idx.begin());
+            if (mid == lo || mid == hi) mid = lo + n / 2;
+        } else if (n > 2) {
+            int axis = 0;
+            for (int k = 1; k < 3; ++k) if (cb.mx[k] - cb.mn[k] > cb.mx[axis] - cb.mn[axis]) axis = k;
+            std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) {
+                return boxes[a].mn[axis] + boxes[a].mx[axis] < boxes[b].mn[axis] + boxes[b].mx[axis];
+            });
+        }
+        HostBvhNode node;
+        node.parent = -1;
+        Box lb, rb;
+        node.left = build(lo, mid, depth + 1, lb);
+        node.right = build(mid, hi, depth + 1, rb);
+        node.box = box_union(lb, rb);
+        int me = (int)out.size();
+        if (node.left >= 0) out[node.left].parent = me;
+        if (node.right >= 0) out[node.right].parent = me;
+        out.push_back(node);
+        box_out = node.box;
+        return me;
+    }
+};
+}  // namespace
+
+// builds the device tree of a BVH hittable; returns the root node index inside `out`
+static int build_device_tree(const SceneBuilder& sb, const HostHittable& b, std::vector<HostBvhNode>& out) {
+    // the primitive set = the leaves of the recorded tree, in left-to-right order
+    std::vector<int> prims;
+    std::vector<int> stack{b.root};
+    while (!stack.empty()) {
+        int i = stack.back(); stack.pop_back();
+        if (i < 0) { int h = ~i; if (prims.empty() || prims.back() != h) prims.push_back(h); continue; }
+        const HostBvhNode& n = b.nodes[i];
+        stack.push_back(n.right);
+        stack.push_back(n.left);
+    }
+    std::vector<Box> boxes(prims.size());
+    for (size_t i = 0; i < prims.size(); ++i)
+        if (!sb.ok_hit(prims[i]) || !sb.bounding_box(prims[i], b.t0, b.t1, boxes[i])) return -1;
+    out.clear();
+    out.reserve(prims.size());
+    SahBuilder sah{prims, boxes, out, {}};
+    sah.idx.resize(prims.size());
+    for (size_t i = 0; i < prims.size(); ++i) sah.idx[i] = (int)i;
+    Box bx;
+    int root = sah.build(0, prims.size(), 0, bx);
+    if (root < 0) {  // a single primitive: a node with one child, like bvh.rs's len == 1 case
+        HostBvhNode node; node.parent = -1; node.left = root; node.right = root; node.box = bx;
+        out.push_back(node);
+        root = 0;
+    }
+    return root;
+}
+
 // ---------------------------------------------------------------------------- Perlin tables
 static void perlin_table(uint32_t seed, uint8_t* perm) {
     for (int i = 0; i < 256; ++i) perm[i] = (uint8_t)i;
@@ -190,6 +316,7 @@ struct Flattener {
     std::unordered_map<int, uint32_t> prim_of;   // hittable id -> prim_ref
     std::unordered_map<int, int> bvh_base;       // hittable id -> first node index
     std::unordered_map<int, int> bvh_pred;       // hittable id -> predictor index
+    std::unordered_map<int, int> bvh_root, bvh_nodes;
     int status = 0;
 
     struct Xf { bool translate = false, rotate = false; float d[3] = {0, 0, 0}; float s = 0, c = 1; int medium = -1; };
@@ -240,6 +367,8 @@ struct Flattener {
             fs.handle[PT_CUBE].push_back(hid);
             break;
         }
+        fs.rank[prim_type(ref)].push_back(0);
+        fs.leaf[prim_type(ref)].push_back(-1);
         prim_of[hid] = ref;
         return ref;
     }
@@ -249,23 +378,38 @@ struct Flattener {
     int add_bvh(int hid) {
         auto it = bvh_base.find(hid);
         if (it != bvh_base.end()) return it->second;
-        const HostHittable& b = sb.hittables[hid];
+        const HostHittable& rec = sb.hittables[hid];
+        // device tree: SAH rebuild by default, the recorded (bvh.rs) topology when asked for
+        HostHittable sah_tree;
+        if (!sb.device_reference_topology) {
+            sah_tree.t0 = rec.t0; sah_tree.t1 = rec.t1; sah_tree.predictor = rec.predictor;
+            sah_tree.root = build_device_tree(sb, rec, sah_tree.nodes);
+            if (sah_tree.root < 0) { fail(SHIM_ERR_UNSUPPORTED_, "a BVH may only contain primitives and cubes"); return -1; }
+            sah_tree.height = bvh_height(sah_tree.nodes, sah_tree.root);
+        }
+        const HostHittable& b = sb.device_reference_topology ? rec : sah_tree;
         int base = (int)fs.nodes.size();
         fs.nodes.resize(base + b.nodes.size());
-        // left-to-right leaf ranks + primitive placement in leaf order (iterative DFS, left first)
-        std::vector<int> rank_base(b.nodes.size(), 0);
+        // in-order walk: primitives are appended to the device arrays in left-to-right leaf order (neighbouring
+        // leaves are neighbours in memory) and get their leaf rank (tie rule of bvh.rs:409-415) and leaf node
+        if (b.height > SHIM_MAX_BVH_HEIGHT) { fail(SHIM_ERR_UNSUPPORTED_, "BVH taller than the traversal stack"); return -1; }
         int rank = 0;
-        // ranks come from a true in-order walk (caller-built trees may mix inner and primitive children)
+        bool bad = false;
         std::function<void(int)> walk = [&](int i) {
             const HostBvhNode& n = b.nodes[i];
             bool dup = n.left < 0 && n.right < 0 && n.left == n.right;
-            if (n.left >= 0) walk(n.left);
-            else { rank_base[i] = rank; rank++; }
-            if (n.right >= 0) walk(n.right);
-            else if (!dup) { if (n.left >= 0) rank_base[i] = rank; rank++; }
+            auto leaf_child = [&](int c) {
+                int h = ~c;
+                if (!sb.ok_hit(h) || !is_prim(sb.hittables[h].kind)) { bad = true; return; }
+                uint32_t ref = add_prim(h);
+                fs.rank[prim_type(ref)][prim_index(ref)] = rank++;
+                fs.leaf[prim_type(ref)][prim_index(ref)] = base + i;
+            };
+            if (n.left >= 0) walk(n.left); else leaf_child(n.left);
+            if (n.right >= 0) walk(n.right); else if (!dup) leaf_child(n.right);
         };
-        if (b.height > SHIM_MAX_BVH_HEIGHT) { fail(SHIM_ERR_UNSUPPORTED_, "BVH taller than the traversal stack"); return -1; }
         walk(b.root);
+        if (bad) { fail(SHIM_ERR_UNSUPPORTED_, "a BVH may only contain primitives and cubes"); return -1; }
         for (size_t i = 0; i < b.nodes.size(); ++i) {
             const HostBvhNode& n = b.nodes[i];
             DevNode dn;
@@ -288,11 +432,12 @@ struct Flattener {
             dn.a = f4{lb.mn[0], lb.mn[1], lb.mn[2], lb.mx[0]};
             dn.b = f4{lb.mx[1], lb.mx[2], rb.mn[0], rb.mn[1]};
             dn.c = f4{rb.mn[2], rb.mx[0], rb.mx[1], rb.mx[2]};
-            // rank of the first primitive child; when only the right child is a primitive the kernel adds 0
-            dn.d = i4{lref, rref, n.parent >= 0 ? base + n.parent : -1, rank_base[i]};
+            dn.d = i4{lref, rref, n.parent >= 0 ? base + n.parent : -1, 0};
             fs.nodes[base + i] = dn;
         }
         bvh_base[hid] = base;
+        bvh_root[hid] = b.root;
+        bvh_nodes[hid] = (int)b.nodes.size();
         if (b.predictor) { bvh_pred[hid] = (int)fs.predictor_bvh.size(); fs.predictor_bvh.push_back(hid); }
         return base;
     }
@@ -305,7 +450,7 @@ struct Flattener {
         if (h.kind == H_BVH) {
             int base = add_bvh(hid);
             if (base < 0) return;
-            ob.kind = OBJ_BVH; ob.ref = base + h.root; ob.n_nodes = (int)h.nodes.size();
+            ob.kind = OBJ_BVH; ob.ref = base + bvh_root[hid]; ob.n_nodes = bvh_nodes[hid];
             if (h.predictor) { ob.flags |= OBJ_PREDICTOR; ob.predictor = bvh_pred[hid]; }
         } else {
             ob.kind = OBJ_PRIM; ob.ref = (int)add_prim(hid);
@@ -389,7 +534,7 @@ SceneView FlatScene::view() const {
     v.msph = msph.data(); v.rect = rect.data(); v.tri = tri.data(); v.cube = cube.data();
     v.objects = objects.data(); v.materials = materials.data(); v.textures = textures.data();
     v.images = images.data(); v.perlin = perlin.data();
-    for (int i = 0; i < 5; ++i) v.handle[i] = handle[i].data();
+    for (int i = 0; i < 5; ++i) { v.handle[i] = handle[i].data(); v.rank[i] = rank[i].data(); v.leaf[i] = leaf[i].data(); }
     v.n_objects = (int)objects.size(); v.n_nodes = (int)nodes.size();
     return v;
 }
@@ -397,7 +542,7 @@ uint64_t FlatScene::bytes() const {
     uint64_t b = nodes.size() * sizeof(DevNode) + sph.size() * 8 + sph_s.size() * 16 + sph_mat.size() * 4 +
                  (msph.size() + rect.size() + tri.size() + cube.size() + materials.size() + textures.size()) * 16 +
                  objects.size() * sizeof(DevObject) + images.size() + perlin.size();
-    for (int i = 0; i < 5; ++i) b += handle[i].size() * 4;
+    for (int i = 0; i < 5; ++i) b += handle[i].size() * 12;
     return b;
 }
 

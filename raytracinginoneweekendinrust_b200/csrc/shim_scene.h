@@ -52,7 +52,7 @@ struct FlatScene {
     std::vector<DevObject> objects;
     std::vector<f4> materials, textures;
     std::vector<uint8_t> images, perlin;
-    std::vector<int> handle[5];
+    std::vector<int> handle[5], rank[5], leaf[5];
     std::vector<int> predictor_bvh;  // hittable id of each BVH that carries a predictor
     SceneView view() const;          // pointers into the host vectors
     uint64_t bytes() const;
@@ -64,6 +64,7 @@ struct SceneBuilder {
     std::vector<HostHittable> hittables;
     std::vector<int> world;
     std::string err;
+    bool device_reference_topology = false;  // walk the recorded bvh.rs tree instead of the SAH rebuild
 
     bool ok_tex(int t) const { return t >= 0 && t < (int)textures.size(); }
     bool ok_mat(int m) const { return m >= 0 && m < (int)materials.size(); }

@@ -61,7 +61,7 @@ struct alignas(16) DevNode {
     f4 a;  // l.min.x l.min.y l.min.z l.max.x
     f4 b;  // l.max.y l.max.z r.min.x r.min.y
     f4 c;  // r.min.z r.max.x r.max.y r.max.z
-    i4 d;  // left ref, right ref (>=0 node, <0 ~prim_ref), parent, left-to-right rank of the first primitive child
+    i4 d;  // left ref, right ref (>=0 node, <0 ~prim_ref), parent, unused
 };
 
 enum ObjFlags { OBJ_TRANSLATE = 1, OBJ_ROTATE = 2, OBJ_MEDIUM = 4, OBJ_PREDICTOR = 8 };
@@ -93,6 +93,8 @@ struct SceneView {
     const uint8_t* images;
     const uint8_t* perlin;
     const int* handle[5];   // device prim index -> user handle, per PrimType
+    const int* rank[5];     // device prim index -> left-to-right leaf rank inside its BVH (ties, bvh.rs:409-415)
+    const int* leaf[5];     // device prim index -> node whose child it is (what HRPP stores, bvh.rs:382/398)
     int n_objects;
     int n_nodes;
 };

@@ -40,7 +40,7 @@ extern "C" __attribute__((visibility("default"))) int hs_trace_closest(shim_scen
         rng_init(rng, (uint32_t)i, 0, seed);
         rng_key(rng, 0, STAGE_INTERSECT);
         TraceCounters tc; tc.nodes = 0; tc.prims = 0;
-        Hit h = closest_hit(sv, r, t_min, t_max, rng, &tc);
+        Hit h = closest_hit<true>(sv, r, t_min, t_max, rng, &tc);
         nodes += tc.nodes; prims += tc.prims;
         prim[i] = hit_handle(sv, h);
         t[i] = h.obj < 0 ? INFINITY : h.t;
@@ -71,7 +71,7 @@ extern "C" __attribute__((visibility("default"))) int hs_sample_radiance(shim_sc
             rng_init(rng, pixel, sample, p->seed);
             rng_key(rng, (uint32_t)bounce, STAGE_INTERSECT);
             ++rays;
-            Hit h = closest_hit(sv, r, 0.001f, INFINITY, rng, nullptr);
+            Hit h = closest_hit<false>(sv, r, 0.001f, INFINITY, rng, nullptr);
             if (h.obj < 0) { L = L + mk3(thr.x * p->background[0], thr.y * p->background[1], thr.z * p->background[2]); break; }
             int mat = hit_material(sv, h);
             int kind = mat_kind(sv, mat);

@@ -72,7 +72,7 @@ def test_render_matches_oracle_same_stream(name):
     assert outlier.sum() <= allowed, f"{outlier.sum()} outlier pixels"
     rmse = float(np.sqrt(np.mean(diff[~outlier] ** 2)))
     assert rmse <= 1e-5, f"rmse {rmse} over non-outlier pixels"
-    assert abs(int(st.rays) - int(so.rays)) <= max(4, so.rays // 2000), (st.rays, so.rays)
+    assert abs(int(st.rays) - int(so.rays)) <= (0 if allowed == 0 else max(8, so.rays // 200)), (st.rays, so.rays)
 
 
 def test_sample_range_and_tile_sharding_compose():
