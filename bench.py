@@ -186,7 +186,8 @@ def main_gpu(args):
     cfg, W, H, spp = workload(args)
     scene = api.Scene()
     info = scenes.build(scene, cfg.scene, seed=1, **scene_kwargs(cfg, args))
-    flags = capi.RENDER_RAW_SUM | capi.RENDER_PROFILE | (capi.RENDER_PREDICTORS if info.predictors else 0)
+    base_flags = capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0)
+    flags = base_flags  # timed steps carry no per-kernel events: recording them costs ~10 % of a step
     total_spp = spp * world
     # weak scaling: rank r renders absolute samples [r*spp, (r+1)*spp) of a total_spp-sample image
     params = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
@@ -195,8 +196,11 @@ def main_gpu(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
-    def step():
-        st = scene.render_device(cfg.camera, params, fb.data_ptr(), stream.cuda_stream)
+    prof_params = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
+                                  sample_count=spp, flags=base_flags | capi.RENDER_PROFILE, pool_paths=args.pool)
+
+    def step(prm=None):
+        st = scene.render_device(cfg.camera, prm or params, fb.data_ptr(), stream.cuda_stream)
         if world > 1:
             dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
         return st
@@ -223,6 +227,12 @@ def main_gpu(args):
         flush.zero_()  # L2 flush between timed steps (outside the event pair)
     barrier()
     wall = time.perf_counter() - wall0
+    # roofline pass: the same step again with CUDA events around every wf_extend launch (on its stream)
+    prof_stats = []
+    for _ in range(args.profile_steps):
+        flush.zero_()
+        prof_stats.append(step(prof_params))
+    barrier()
     clocks = sampler.stop() if rank == 0 else {}
     ms = [a.elapsed_time(b) for a, b in ev]
     tot_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
@@ -276,9 +286,10 @@ def main_gpu(args):
         prims_per_ray = st_cnt.prim_tests / max(1, st_cnt.rays)
         prim_bytes = {"random-spheres": 32, "cornell-smoke": 32, "showcase": 32}.get(cfg.scene, 48)
         bytes_per_ray = nodes_per_ray * 64 + prims_per_ray * prim_bytes + 128
-        ext_ms = sum(s.extend_ms for s in stats)
-        ext_launch = sum(s.extend_launches for s in stats)
-        rays_rank0 = sum(s.rays for s in stats)
+        ext_ms = sum(s.extend_ms for s in prof_stats)
+        ext_launch = sum(s.extend_launches for s in prof_stats)
+        rays_rank0 = sum(s.rays for s in prof_stats)
+        prof_ms = sum(s.device_ms for s in prof_stats)
         peak, peak_src, sm_max = load_peaks()
         achieved = bytes_per_ray * rays_rank0 / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
         sm_clk = (clocks.get("sm_mhz") or sm_max) * 1e6
@@ -287,8 +298,10 @@ def main_gpu(args):
         roofline = {"bound": "hbm", "kernel": "wf_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "prims_per_ray": prims_per_ray,
-                    "extend_ms_per_step": ext_ms / args.steps, "extend_share_of_step": ext_ms / sum(ms),
-                    "extend_launches_per_step": ext_launch / args.steps,
+                    "extend_ms_per_step": ext_ms / max(1, len(prof_stats)), "extend_share_of_step": ext_ms / prof_ms if prof_ms else None,
+                    "extend_launches_per_step": ext_launch / max(1, len(prof_stats)),
+                    "measured_on": f"{len(prof_stats)} extra steps of the same workload right after the timed steps, CUDA events around every "
+                                   "wf_extend launch (the timed steps carry no per-kernel events)",
                     "note": "scene data is L1/L2 resident (KB-sized); the binding ceiling is instruction issue, see issue_roofline",
                     "issue_roofline": {"budget_inst_per_ray": inst_per_ray, "sm_mhz": sm_clk / 1e6,
                                        "peak_mrays": issue_peak, "achieved_mrays_extend_only": rays_rank0 / (ext_ms / 1e3) / 1e6 if ext_ms > 0 else None,
@@ -301,7 +314,7 @@ def main_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(tot_ms.item()) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (+f64 sphere quadratic)", "data": "synthetic",
-                "config": config_dict(cfg, W, H, spp, args, {"sharding": f"sample-range x{world}", "pool_paths": args.pool or (1 << 22),
+                "config": config_dict(cfg, W, H, spp, args, {"sharding": f"sample-range x{world}", "pool_paths": args.pool or (1 << 23),
                                                              "scene_device_bytes": scene.device_bytes()}),
                 "samples_per_s": samples_per_s, "rays_per_step": float(rays.item()) / args.steps,
                 "wall_s_timed_region": wall,
@@ -329,7 +342,8 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--tris", type=int, default=0)
     ap.add_argument("--pool", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--steps-cpu", type=int, default=2)
     ap.add_argument("--warmup-cpu", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")

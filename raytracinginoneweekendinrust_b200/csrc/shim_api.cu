@@ -67,8 +67,8 @@ struct DeviceScene {
 
 struct Wavefront {
     uint32_t pool = 0;
-    DevBuf<f4> ray_o[2], ray_d[2], thr[2], hit;
-    DevBuf<uint32_t> samp[2], mq[MAT_KINDS], cnt;
+    DevBuf<f4> ray_o[2], ray_d[2], thr[2], mq_o, mq_d, mq_thr, mq_hit;
+    DevBuf<uint32_t> cnt;
     DevBuf<float> accum;
     DevBuf<uint32_t> pix_table;
     int pt_key[6] = {0, 0, 0, 0, 0, 0};
@@ -79,9 +79,8 @@ struct Wavefront {
     int max_smem = 0;
     std::vector<cudaEvent_t> prof;  // event pairs around wf_extend launches (SHIM_RENDER_PROFILE)
     void release() {
-        for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); samp[i].release(); }
-        hit.release(); cnt.release(); accum.release(); pix_table.release();
-        for (auto& q : mq) q.release();
+        for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); }
+        mq_o.release(); mq_d.release(); mq_thr.release(); mq_hit.release(); cnt.release(); accum.release(); pix_table.release();
         if (h_flags) cudaFreeHost(h_flags);
         h_flags = nullptr;
         if (ev0) cudaEventDestroy(ev0);
@@ -173,14 +172,14 @@ SHIM_API int shim_commit(shim_scene* s) {
 // ------------------------------------------------------------------------------------------ render
 static int wf_prepare(shim_scene* s, const shim_render_params& p) {
     Wavefront& w = g_wf[s->dev->device & 63];
-    uint32_t pool = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 22);
+    uint32_t pool = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 23);
     const char* env = getenv("SHIM_POOL_PATHS");
     if (p.pool_paths <= 0 && env && atoi(env) > 0) pool = (uint32_t)atoi(env);
     pool = (pool + 31u) & ~31u;
     if (w.pool != pool) {
-        for (int i = 0; i < 2; ++i) { CU(w.ray_o[i].alloc(pool)); CU(w.ray_d[i].alloc(pool)); CU(w.thr[i].alloc(pool)); CU(w.samp[i].alloc(pool)); }
-        CU(w.hit.alloc(pool));
-        for (int k = 0; k < MAT_KINDS; ++k) CU(w.mq[k].alloc(pool));
+        for (int i = 0; i < 2; ++i) { CU(w.ray_o[i].alloc(pool)); CU(w.ray_d[i].alloc(pool)); CU(w.thr[i].alloc(pool)); }
+        CU(w.mq_o.alloc((size_t)pool * MAT_KINDS)); CU(w.mq_d.alloc((size_t)pool * MAT_KINDS));
+        CU(w.mq_thr.alloc((size_t)pool * MAT_KINDS)); CU(w.mq_hit.alloc((size_t)pool * MAT_KINDS));
         CU(w.cnt.alloc(CNT_WORDS));
         if (!w.h_flags) CU(cudaMallocHost(&w.h_flags, 64 * sizeof(uint32_t)));
         if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); CU(cudaEventCreate(&w.ev_chunk[0])); CU(cudaEventCreate(&w.ev_chunk[1])); }
@@ -198,7 +197,7 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         w.grid_shade = sms * (per_sm > 0 ? per_sm : 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
         w.grid_generate = sms * (per_sm > 0 ? per_sm : 1);
-        w.grid_tail = sms;
+        w.grid_tail = sms * 2;
     }
     size_t fb = (size_t)p.width * p.height * 3;
     if (w.accum.n != fb) CU(w.accum.alloc(fb));
@@ -233,6 +232,9 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         p.sample_count < 0 || p.sample_begin < 0 || (p.tile_world > 1 && (p.tile_rank < 0 || p.tile_rank >= p.tile_world)))
         return set_err(SHIM_ERR_INVALID, "shim_render: bad render params");
     if ((uint64_t)p.width * (uint64_t)p.height > 0x7fffffffull) return set_err(SHIM_ERR_INVALID, "shim_render: image too large");
+    if (p.max_depth > 255) return set_err(SHIM_ERR_UNSUPPORTED, "shim_render: max_depth above 255 (the bounce is carried in 8 bits of the ray record)");
+    if ((int64_t)p.sample_begin + (p.sample_count > 0 ? p.sample_count : p.samples_per_pixel) > (1 << 24))
+        return set_err(SHIM_ERR_UNSUPPORTED, "shim_render: absolute sample index above 2^24 (carried in 24 bits of the ray record)");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = wf_prepare(s, p);
     if (rc < 0) return rc;
@@ -243,9 +245,8 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     k.sv = s->dev->scene.view;
     camera_new(cam->look_from, cam->look_at, cam->view_up, cam->vertical_fov, cam->aspect_ratio, cam->aperture, cam->focus_dist,
                cam->time_start, cam->time_end, k.cam);
-    for (int i = 0; i < 2; ++i) { k.ray_o[i] = w.ray_o[i].p; k.ray_d[i] = w.ray_d[i].p; k.thr[i] = w.thr[i].p; k.samp[i] = w.samp[i].p; }
-    k.hit = w.hit.p;
-    for (int q = 0; q < MAT_KINDS; ++q) k.mq[q] = w.mq[q].p;
+    for (int i = 0; i < 2; ++i) { k.ray_o[i] = w.ray_o[i].p; k.ray_d[i] = w.ray_d[i].p; k.thr[i] = w.thr[i].p; }
+    k.mq_o = w.mq_o.p; k.mq_d = w.mq_d.p; k.mq_thr = w.mq_thr.p; k.mq_hit = w.mq_hit.p;
     k.cnt = w.cnt.p; k.accum = w.accum.p; k.pix_table = w.pix_table.p;
     k.npix = w.npix;
     int count = p.sample_count > 0 ? p.sample_count : p.samples_per_pixel;

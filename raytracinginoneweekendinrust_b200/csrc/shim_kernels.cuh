@@ -9,11 +9,13 @@
 //   wf_extend    closest hit for every queued ray (hittable.rs:100-118).  The BVH nodes and
 //                primitive arrays are staged into shared memory by TMA bulk copies
 //                (cp.async.bulk + mbarrier) when they fit, so the walk's 16-byte node fetches
-//                are LDS; misses add the background on the spot; hits are binned into
-//                per-material queues with one atomic per warp and material
-//   wf_shade     one launch covering the five material queues (each 256-ray chunk of a queue is
-//                shaded by code specialised for that material): rebuild the HitRecord, emit,
-//                scatter, and append the continuing ray to the next queue (warp-ballot compaction)
+//                are LDS; misses add the background on the spot; a hit appends the ray and its
+//                hit record to the queue of its material kind (warp match.any: one atomic per
+//                group of lanes that hit the same kind)
+//   wf_shade     material-sorted shading, one launch covering the five material queues: each
+//                256-ray chunk of a queue is streamed (coalesced) through code specialised for
+//                that material: rebuild the HitRecord, emit, scatter, and append the continuing
+//                ray to the next ray queue (warp-ballot compaction, one atomic per warp)
 //   wf_tail      once no samples are left to start and only a few thousand paths are alive, one
 //                launch finishes them (extend + shade in a loop per thread) instead of ~40
 //                near-empty iterations
@@ -43,11 +45,11 @@ struct WfParams {
     CameraPod cam;
     // ray queues (double buffered)
     f4* ray_o[2];   // origin.xyz, time
-    f4* ray_d[2];   // direction.xyz, bounce (int bits)
+    f4* ray_d[2];   // direction.xyz, bounce | sample << 8 (int bits)
     f4* thr[2];     // throughput.rgb, pixel index (int bits)
-    uint32_t* samp[2];
-    f4* hit;        // t, obj | face << 16, prim_ref, material
-    uint32_t* mq[MAT_KINDS];
+    // material queues carry the payload: kind k occupies [k * pool, (k + 1) * pool) of each array
+    f4* mq_o; f4* mq_d; f4* mq_thr;
+    f4* mq_hit;     // t, obj | face << 16, prim_ref, material
     uint32_t* cnt;
     float* accum;   // W*H*3 radiance sums
     const uint32_t* pix_table;
@@ -129,12 +131,11 @@ __global__ void __launch_bounds__(256) wf_generate(WfParams p, int cur) {
         Ray r = camera_sample(p.cam, x, y, p.width, p.height, rng);
         uint32_t slot = n_cur + j;
         f4 o; o.x = r.o.x; o.y = r.o.y; o.z = r.o.z; o.w = r.time;
-        f4 d; d.x = r.d.x; d.y = r.d.y; d.z = r.d.z; d.w = i2f(0);
+        f4 d; d.x = r.d.x; d.y = r.d.y; d.z = r.d.z; d.w = i2f((int)(sample << 8));
         f4 t; t.x = 1.0f; t.y = 1.0f; t.z = 1.0f; t.w = i2f((int)pixel);
         p.ray_o[cur][slot] = o;
         p.ray_d[cur][slot] = d;
         p.thr[cur][slot] = t;
-        p.samp[cur][slot] = sample;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -159,17 +160,19 @@ __global__ void __launch_bounds__(256) wf_generate(WfParams p, int cur) {
 template <bool COUNT, bool MEDIA>
 __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& sv, int cur, uint32_t n) {
     const uint32_t n_round = (n + 31u) & ~31u;
+    const uint32_t lane = threadIdx.x & 31u;
     uint32_t nodes = 0, prims = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        const bool valid = i < n;
-        int kind = -1;
-        if (valid) {
-            f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i];
+        int kind = 7;
+        f4 o, d, t, hv;
+        if (i < n) {
+            o = p.ray_o[cur][i]; d = p.ray_d[cur][i]; t = p.thr[cur][i];
             Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
             Rng rng;
             if (MEDIA) {
-                rng_init(rng, (uint32_t)f2i(p.thr[cur][i].w), p.samp[cur][i], p.seed);
-                rng_key(rng, (uint32_t)f2i(d.w), STAGE_INTERSECT);
+                uint32_t bs = (uint32_t)f2i(d.w);
+                rng_init(rng, (uint32_t)f2i(t.w), bs >> 8, p.seed);
+                rng_key(rng, bs & 255u, STAGE_INTERSECT);
             } else {
                 rng_init(rng, 0, 0, 0);
             }
@@ -178,7 +181,6 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
             nodes += tc.nodes; prims += tc.prims;
             if (h.obj < 0) {  // ray.rs:60: miss returns the background
                 if (p.bg[0] != 0.0f || p.bg[1] != 0.0f || p.bg[2] != 0.0f) {
-                    f4 t = p.thr[cur][i];
                     float* a = p.accum + 3 * (size_t)(uint32_t)f2i(t.w);
                     atomicAdd(a + 0, t.x * p.bg[0]);
                     atomicAdd(a + 1, t.y * p.bg[1]);
@@ -187,14 +189,18 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
             } else {
                 int mat = hit_material(sv, h);
                 kind = mat_kind(sv, mat);
-                f4 hv; hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat);
-                p.hit[i] = hv;
+                hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat);
             }
         }
-#pragma unroll
-        for (int k = 0; k < MAT_KINDS; ++k) {
-            uint32_t pos = warp_append(p.cnt + CNT_MQ + k, kind == k);
-            if (kind == k) p.mq[k][pos] = i;
+        // append to the material queue: lanes that hit the same kind share one atomic
+        unsigned grp = __match_any_sync(0xffffffffu, kind);
+        if (kind < MAT_KINDS) {
+            int leader = __ffs(grp) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(p.cnt + CNT_MQ + kind, (uint32_t)__popc(grp));
+            base = __shfl_sync(grp, base, leader);
+            size_t pos = (size_t)kind * p.pool + base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+            p.mq_o[pos] = o; p.mq_d[pos] = d; p.mq_thr[pos] = t; p.mq_hit[pos] = hv;
         }
     }
     if (COUNT) {
@@ -272,26 +278,24 @@ __device__ __forceinline__ void shade_chunk(const WfParams& p, int cur, uint32_t
     const int nxt = 1 - cur;
     ShadeOut so;
     so.cont = false; so.ray.o = mk3(0, 0, 0); so.ray.d = mk3(0, 0, 0); so.ray.time = 0; so.thr = mk3(0, 0, 0);
-    int bounce = 0; uint32_t pixel = 0, sample = 0;
+    uint32_t bs = 0, pixel = 0;
     if (j < n) {
-        uint32_t i = p.mq[KIND][j];
-        f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i], t = p.thr[cur][i], hv = p.hit[i];
-        sample = p.samp[cur][i];
+        size_t q = (size_t)KIND * p.pool + j;
+        f4 o = p.mq_o[q], d = p.mq_d[q], t = p.mq_thr[q], hv = p.mq_hit[q];
         Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
-        bounce = f2i(d.w); pixel = (uint32_t)f2i(t.w);
+        bs = (uint32_t)f2i(d.w); pixel = (uint32_t)f2i(t.w);
         Hit h; h.t = hv.x; h.obj = f2i(hv.y) & 0xffff; h.face = f2i(hv.y) >> 16; h.prim = (uint32_t)f2i(hv.z);
-        shade_one<KIND>(p, p.sv, r, h, f2i(hv.w), mk3(t.x, t.y, t.z), bounce, pixel, sample, so);
+        shade_one<KIND>(p, p.sv, r, h, f2i(hv.w), mk3(t.x, t.y, t.z), (int)(bs & 255u), pixel, bs >> 8, so);
     }
     if (KIND != MAT_DIFFUSE_LIGHT) {
         uint32_t pos = warp_append(p.cnt + nxt, so.cont);
         if (so.cont) {
             f4 o; o.x = so.ray.o.x; o.y = so.ray.o.y; o.z = so.ray.o.z; o.w = so.ray.time;
-            f4 d; d.x = so.ray.d.x; d.y = so.ray.d.y; d.z = so.ray.d.z; d.w = i2f(bounce + 1);
+            f4 d; d.x = so.ray.d.x; d.y = so.ray.d.y; d.z = so.ray.d.z; d.w = i2f((int)(bs + 1u));
             f4 t; t.x = so.thr.x; t.y = so.thr.y; t.z = so.thr.z; t.w = i2f((int)pixel);
             p.ray_o[nxt][pos] = o;
             p.ray_d[nxt][pos] = d;
             p.thr[nxt][pos] = t;
-            p.samp[nxt][pos] = sample;
         }
     }
 }
@@ -325,10 +329,10 @@ __global__ void __launch_bounds__(128) wf_tail(WfParams p, int cur) {
     uint32_t traced = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         f4 o = p.ray_o[nxt][i], d = p.ray_d[nxt][i], t = p.thr[nxt][i];
-        uint32_t sample = p.samp[nxt][i], pixel = (uint32_t)f2i(t.w);
+        uint32_t sample = (uint32_t)f2i(d.w) >> 8, pixel = (uint32_t)f2i(t.w);
         Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
         f3 thr = mk3(t.x, t.y, t.z);
-        for (int bounce = f2i(d.w); bounce < p.max_depth; ++bounce) {
+        for (int bounce = f2i(d.w) & 255; bounce < p.max_depth; ++bounce) {
             Rng rng;
             rng_init(rng, pixel, sample, p.seed);
             rng_key(rng, (uint32_t)bounce, STAGE_INTERSECT);
