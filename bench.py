@@ -171,7 +171,7 @@ def main_reference(args):
 def main_gpu(args):
     import torch
     import torch.distributed as dist
-    from raytracinginoneweekendinrust_b200 import api, capi, scenes
+    from raytracinginoneweekendinrust_b200 import api, capi, distributed, scenes
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,6 +190,7 @@ def main_gpu(args):
     flags = base_flags  # timed steps carry no per-kernel events: recording them costs ~10 % of a step
     total_spp = spp * world
     # weak scaling: rank r renders absolute samples [r*spp, (r+1)*spp) of a total_spp-sample image
+    assert distributed.shard_samples(total_spp, rank, world) == (rank * spp, spp)
     params = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
                              sample_count=spp, flags=flags, pool_paths=args.pool)
     fb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
@@ -201,8 +202,7 @@ def main_gpu(args):
 
     def step(prm=None):
         st = scene.render_device(cfg.camera, prm or params, fb.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
+        distributed.reduce_framebuffer(fb, total_spp, dst=0) if world > 1 else None  # one framebuffer sum over NVLink
         return st
 
     def barrier():
@@ -252,7 +252,8 @@ def main_gpu(args):
     p_e2e = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
                             sample_count=spp, flags=capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0),
                             pool_paths=args.pool)
-    for k in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
+    E2E_WARM = 2
+    for k in range(args.e2e_steps + E2E_WARM if args.e2e_steps > 0 else 0):
         s2 = api.Scene()
         scenes.SCENES[cfg.scene](s2, seed=1, **scene_kwargs(cfg, args))  # host-side recording (untimed)
         barrier()
@@ -264,7 +265,7 @@ def main_gpu(args):
         if os.environ.get("BENCH_DEBUG"):
             print(f"e2e step {k}: commit {1e3 * (tc - t0):.2f} ms, render {1e3 * (time.perf_counter() - tc):.2f} ms "
                   f"(device {st2.device_ms:.2f} ms, {st2.iterations} iterations)", file=sys.stderr)
-        if k > 0:  # first one warms the allocator / pool
+        if k >= E2E_WARM:  # the first ones warm the pinned staging buffer / allocator
             e2e_ms.append(dt * 1e3)
             e2e_rays += st2.rays
         h2d = s2.device_bytes() + W * H * 4

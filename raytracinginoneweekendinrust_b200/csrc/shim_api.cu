@@ -45,31 +45,24 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// A committed scene is ONE device allocation filled by ONE host-to-device copy: the arrays are packed
+// back to back (256-byte aligned) in a host staging blob first.
 struct DeviceScene {
-    DevBuf<DevNode> nodes;
-    DevBuf<double> sph;
-    DevBuf<f4> sph_s, msph, rect, tri, cube, materials, textures;
-    DevBuf<int> sph_mat;
-    DevBuf<DevObject> objects;
-    DevBuf<uint8_t> images, perlin;
-    DevBuf<int> handle[5], rank[5], leaf[5];
+    unsigned char* base = nullptr;
+    size_t bytes_alloc = 0;
     SceneView view;
     SmemLayout smem;
     uint64_t bytes = 0;
-    void release() {
-        nodes.release(); sph.release(); sph_s.release(); msph.release(); rect.release(); tri.release(); cube.release();
-        materials.release(); textures.release(); sph_mat.release(); objects.release(); images.release(); perlin.release();
-        for (auto& h : handle) h.release();
-        for (auto& h : rank) h.release();
-        for (auto& h : leaf) h.release();
-    }
+    void release() { if (base) cudaFree(base); base = nullptr; bytes_alloc = 0; }
 };
 
 struct Wavefront {
     uint32_t pool = 0;
     DevBuf<f4> ray_o[2], ray_d[2], thr[2], mq_o, mq_d, mq_thr, mq_hit;
     DevBuf<uint32_t> cnt;
-    DevBuf<float> accum;
+    DevBuf<float> accum, d_out;
+    float* h_out = nullptr;  // pinned staging for the host framebuffer
+    size_t h_out_n = 0;
     DevBuf<uint32_t> pix_table;
     int pt_key[6] = {0, 0, 0, 0, 0, 0};
     uint32_t npix = 0;
@@ -82,6 +75,8 @@ struct Wavefront {
         for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); }
         mq_o.release(); mq_d.release(); mq_thr.release(); mq_hit.release(); cnt.release(); accum.release(); pix_table.release();
         if (h_flags) cudaFreeHost(h_flags);
+        if (h_out) cudaFreeHost(h_out);
+        h_out = nullptr; h_out_n = 0; d_out.release();
         h_flags = nullptr;
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -132,17 +127,41 @@ SHIM_API int shim_commit(shim_scene* s) {
     if (rc < 0) return rc;
     const FlatScene& f = s->flat;
     DeviceScene& d = s->dev->scene;
-    CU(d.nodes.upload(f.nodes)); CU(d.sph.upload(f.sph)); CU(d.sph_s.upload(f.sph_s)); CU(d.sph_mat.upload(f.sph_mat));
-    CU(d.msph.upload(f.msph)); CU(d.rect.upload(f.rect)); CU(d.tri.upload(f.tri)); CU(d.cube.upload(f.cube));
-    CU(d.objects.upload(f.objects)); CU(d.materials.upload(f.materials)); CU(d.textures.upload(f.textures));
-    CU(d.images.upload(f.images)); CU(d.perlin.upload(f.perlin));
-    for (int i = 0; i < 5; ++i) { CU(d.handle[i].upload(f.handle[i])); CU(d.rank[i].upload(f.rank[i])); CU(d.leaf[i].upload(f.leaf[i])); }
+    std::vector<unsigned char> blob;
+    auto put = [&](const void* src, size_t bytes) -> size_t {
+        size_t off = (blob.size() + 255) & ~(size_t)255;
+        blob.resize(off + (bytes ? bytes : 16));
+        if (bytes) memcpy(blob.data() + off, src, bytes);
+        return off;
+    };
+    size_t o_nodes = put(f.nodes.data(), f.nodes.size() * sizeof(DevNode));
+    size_t o_sph = put(f.sph.data(), f.sph.size() * 8), o_sph_s = put(f.sph_s.data(), f.sph_s.size() * 16);
+    size_t o_sph_mat = put(f.sph_mat.data(), f.sph_mat.size() * 4);
+    size_t o_msph = put(f.msph.data(), f.msph.size() * 16), o_rect = put(f.rect.data(), f.rect.size() * 16);
+    size_t o_tri = put(f.tri.data(), f.tri.size() * 16), o_cube = put(f.cube.data(), f.cube.size() * 16);
+    size_t o_obj = put(f.objects.data(), f.objects.size() * sizeof(DevObject));
+    size_t o_mat = put(f.materials.data(), f.materials.size() * 16), o_tex = put(f.textures.data(), f.textures.size() * 16);
+    size_t o_img = put(f.images.data(), f.images.size()), o_perlin = put(f.perlin.data(), f.perlin.size());
+    size_t o_handle[5], o_rank[5], o_leaf[5];
+    for (int i = 0; i < 5; ++i) {
+        o_handle[i] = put(f.handle[i].data(), f.handle[i].size() * 4);
+        o_rank[i] = put(f.rank[i].data(), f.rank[i].size() * 4);
+        o_leaf[i] = put(f.leaf[i].data(), f.leaf[i].size() * 4);
+    }
+    d.release();
+    CU(cudaMalloc(&d.base, blob.size()));
+    d.bytes_alloc = blob.size();
+    CU(cudaMemcpy(d.base, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     SceneView& v = d.view;
     memset(&v, 0, sizeof v);
-    v.nodes = d.nodes.p; v.sph = d.sph.p; v.sph_s = d.sph_s.p; v.sph_mat = d.sph_mat.p; v.msph = d.msph.p; v.rect = d.rect.p;
-    v.tri = d.tri.p; v.cube = d.cube.p; v.objects = d.objects.p; v.materials = d.materials.p; v.textures = d.textures.p;
-    v.images = d.images.p; v.perlin = d.perlin.p;
-    for (int i = 0; i < 5; ++i) { v.handle[i] = d.handle[i].p; v.rank[i] = d.rank[i].p; v.leaf[i] = d.leaf[i].p; }
+    v.nodes = (const DevNode*)(d.base + o_nodes); v.sph = (const double*)(d.base + o_sph); v.sph_s = (const f4*)(d.base + o_sph_s);
+    v.sph_mat = (const int*)(d.base + o_sph_mat); v.msph = (const f4*)(d.base + o_msph); v.rect = (const f4*)(d.base + o_rect);
+    v.tri = (const f4*)(d.base + o_tri); v.cube = (const f4*)(d.base + o_cube); v.objects = (const DevObject*)(d.base + o_obj);
+    v.materials = (const f4*)(d.base + o_mat); v.textures = (const f4*)(d.base + o_tex);
+    v.images = d.base + o_img; v.perlin = d.base + o_perlin;
+    for (int i = 0; i < 5; ++i) {
+        v.handle[i] = (const int*)(d.base + o_handle[i]); v.rank[i] = (const int*)(d.base + o_rank[i]); v.leaf[i] = (const int*)(d.base + o_leaf[i]);
+    }
     v.n_objects = (int)f.objects.size(); v.n_nodes = (int)f.nodes.size();
     d.bytes = f.bytes();
     {   // shared-memory image of what wf_extend walks; total = 0 when it cannot fit any sm_100a block
@@ -346,15 +365,23 @@ SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_rende
     if (!s->committed) return set_err(SHIM_ERR_STATE, "shim_render: scene not committed");
     if (p->width < 2 || p->height < 2) return set_err(SHIM_ERR_INVALID, "shim_render: bad render params");
     size_t fb = (size_t)p->width * p->height * 3;
-    float* d_out = nullptr;
-    CU(cudaMalloc(&d_out, fb * sizeof(float)));
-    int rc = shim_render_device(s, cam, p, d_out, stats, nullptr);
-    if (rc == SHIM_OK) {
-        cudaError_t e = cudaMemcpy(out, d_out, fb * sizeof(float), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = set_err(SHIM_ERR_CUDA, std::string("framebuffer copy: ") + cudaGetErrorString(e));
+    int rc = ensure_device(s);
+    if (rc < 0) return rc;
+    Wavefront& w = g_wf[s->dev->device & 63];
+    // persistent device framebuffer + pinned staging: no allocation on the per-call path
+    if (w.d_out.n < fb) CU(w.d_out.alloc(fb));
+    if (w.h_out_n < fb) {
+        if (w.h_out) cudaFreeHost(w.h_out);
+        w.h_out = nullptr; w.h_out_n = 0;
+        CU(cudaMallocHost(&w.h_out, fb * sizeof(float)));
+        w.h_out_n = fb;
     }
-    cudaFree(d_out);
-    return rc;
+    rc = shim_render_device(s, cam, p, w.d_out.p, stats, nullptr);
+    if (rc != SHIM_OK) return rc;
+    CU(cudaMemcpyAsync(w.h_out, w.d_out.p, fb * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaStreamSynchronize(nullptr));
+    memcpy(out, w.h_out, fb * sizeof(float));
+    return SHIM_OK;
 }
 
 // ------------------------------------------------------------------------------------------ gate 1

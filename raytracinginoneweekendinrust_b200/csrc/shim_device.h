@@ -60,8 +60,8 @@ SHIM_HD void rng_init(Rng& r, uint32_t pixel, uint32_t sample, uint64_t seed) {
     r.b0 = r.b1 = r.b2 = r.b3 = 0;
 }
 SHIM_HD void rng_key(Rng& r, uint32_t bounce, uint32_t stage) { r.dim = bounce * 4u + stage; r.j = 0; }
-SHIM_HD void rng_refill(Rng& r) {
-    uint32_t c0 = r.pixel, c1 = r.sample, c2 = r.dim, c3 = r.j >> 2, k0 = r.k0, k1 = r.k1;
+SHIM_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t& o0, uint32_t& o1,
+                           uint32_t& o2, uint32_t& o3) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -69,8 +69,10 @@ SHIM_HD void rng_refill(Rng& r) {
         c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    r.b0 = c0; r.b1 = c1; r.b2 = c2; r.b3 = c3;
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
+// counter = (pixel, sample, bounce * 4 + stage, block index), key = seed
+SHIM_HD void rng_refill(Rng& r) { philox4x32_10(r.pixel, r.sample, r.dim, r.j >> 2, r.k0, r.k1, r.b0, r.b1, r.b2, r.b3); }
 SHIM_HD uint32_t rng_u32(Rng& r) {
     uint32_t lane = r.j & 3u;
     if (lane == 0) rng_refill(r);
@@ -338,8 +340,10 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
             uint32_t ref = ~(uint32_t)cur;
             float t; int face = 0;
             if (COUNT) cnt->prims++;
-            if (hit_prim(sv, ref, c, t_min, best.t, t, face)) {
-                // accepted t <= best.t; an exact tie goes to the later leaf (bvh.rs:409-415)
+            // the primitive sees the widened bound too (an identical sphere's f64 root can lie just above the
+            // f32-rounded best.t); what counts is its f32 t: closer wins, an exact tie goes to the later leaf
+            // of the recorded tree (bvh.rs:409-415), anything beyond best.t is not a hit
+            if (hit_prim(sv, ref, c, t_min, t_cull, t, face) && !(t > best.t)) {
                 bool take = !best.any || t < best.t ||
                             table_of(sv.rank, prim_type(ref))[prim_index(ref)] > table_of(sv.rank, prim_type(best.prim))[prim_index(best.prim)];
                 if (take) { best.t = t; best.prim = ref; best.face = face; best.any = true; t_cull = t + fabsf(t) * 3.8146973e-06f; }

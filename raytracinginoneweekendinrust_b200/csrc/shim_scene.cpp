@@ -393,7 +393,19 @@ struct Flattener {
         // in-order walk: primitives are appended to the device arrays in left-to-right leaf order (neighbouring
         // leaves are neighbours in memory) and get their leaf rank (tie rule of bvh.rs:409-415) and leaf node
         if (b.height > SHIM_MAX_BVH_HEIGHT) { fail(SHIM_ERR_UNSUPPORTED_, "BVH taller than the traversal stack"); return -1; }
-        int rank = 0;
+        // ties (bvh.rs:409-415) go to the primitive that is latest in the left-to-right leaf order of the RECORDED
+        // bvh.rs tree, whichever tree the device walks
+        std::unordered_map<int, int> ref_rank;
+        {
+            int r = 0;
+            std::vector<int> st{rec.root};
+            while (!st.empty()) {
+                int i = st.back(); st.pop_back();
+                if (i < 0) { ref_rank[~i] = r++; continue; }   // a duplicated single-object leaf keeps its later rank
+                st.push_back(rec.nodes[i].right);
+                st.push_back(rec.nodes[i].left);
+            }
+        }
         bool bad = false;
         std::function<void(int)> walk = [&](int i) {
             const HostBvhNode& n = b.nodes[i];
@@ -402,7 +414,7 @@ struct Flattener {
                 int h = ~c;
                 if (!sb.ok_hit(h) || !is_prim(sb.hittables[h].kind)) { bad = true; return; }
                 uint32_t ref = add_prim(h);
-                fs.rank[prim_type(ref)][prim_index(ref)] = rank++;
+                fs.rank[prim_type(ref)][prim_index(ref)] = ref_rank[h];
                 fs.leaf[prim_type(ref)][prim_index(ref)] = base + i;
             };
             if (n.left >= 0) walk(n.left); else leaf_child(n.left);

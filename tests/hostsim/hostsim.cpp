@@ -99,8 +99,5 @@ extern "C" __attribute__((visibility("default"))) void hs_texture_value(shim_sce
 }
 
 extern "C" __attribute__((visibility("default"))) void hs_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
-    Rng r;
-    r.pixel = ctr[0]; r.sample = ctr[1]; r.dim = ctr[2]; r.j = ctr[3] << 2; r.k0 = key[0]; r.k1 = key[1];
-    rng_refill(r);
-    out[0] = r.b0; out[1] = r.b1; out[2] = r.b2; out[3] = r.b3;
+    philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out[0], out[1], out[2], out[3]);
 }

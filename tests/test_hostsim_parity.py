@@ -1,0 +1,83 @@
+"""The product's device arithmetic (csrc/shim_device.h), compiled for the CPU by tests/hostsim, against
+the oracle — the same comparison the -m gpu tests make through the CUDA kernels, runnable without a GPU.
+Both sides are IEEE f32/f64 without contraction, so wherever no transcendental is involved they must agree
+bit for bit, on either device tree (SAH rebuild or the recorded bvh.rs topology)."""
+import numpy as np
+import pytest
+
+import support
+from raytracinginoneweekendinrust_b200 import api, scenes
+import test_gpu_parity as T
+
+
+@pytest.mark.parametrize("reference_tree", [False, True])
+@pytest.mark.parametrize("name", list(scenes.SCENES))
+def test_device_math_matches_oracle(name, reference_tree):
+    kw = T.SMALL.get(name, {})
+    o, h = support.OracleScene(), support.HostSimScene()
+    info = scenes.build(o, name, seed=1, **kw)
+    h.set_device_bvh(reference_tree)
+    scenes.build(h, name, seed=1, **kw)
+    cam = T.CAMERAS[name]
+    W, H, spp = 120, 90, 4
+    xys = support.random_xys(W, H, spp, 1500, seed=4)
+    po = o.params(W, H, spp, 50, background=info.background, seed=13, iterative=True)
+    rays = o.record_path_rays(cam, po, xys, 20000)
+    p_ref, t_ref = o.trace_closest(rays, seed=13)
+    p_dev, t_dev = h.trace_closest(rays, seed=13)
+    np.testing.assert_array_equal(p_ref, p_dev)                       # gate 1: same primitive id
+    hit = p_ref >= 0
+    np.testing.assert_array_equal(t_ref[hit].view(np.uint32), t_dev[hit].view(np.uint32))   # and bit-equal t
+    r_ref, n_ref = o.sample_radiance(cam, po, xys)
+    r_dev, n_dev = h.sample_radiance(cam, api.make_params(W, H, spp, 50, background=info.background, seed=13), xys)
+    assert n_ref == n_dev
+    np.testing.assert_array_equal(r_ref.view(np.uint32), r_dev.view(np.uint32))
+
+
+def test_recursive_and_iterative_integrators_agree():
+    """ray.rs:32-62 recursion vs the wavefront's iterative form: same samples, products associated differently."""
+    o = support.OracleScene()
+    info = scenes.build(o, "random-spheres", seed=1)
+    cam = T.CAMERAS["random-spheres"]
+    xys = support.random_xys(200, 150, 8, 4000, seed=9)
+    a, _ = o.sample_radiance(cam, o.params(200, 150, 8, 50, background=info.background, seed=1, iterative=True), xys)
+    b, _ = o.sample_radiance(cam, o.params(200, 150, 8, 50, background=info.background, seed=1, iterative=False), xys)
+    np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-7)
+
+
+def test_ties_go_to_the_later_leaf():
+    """bvh.rs:409-415 (`left.t < right.t` else right): duplicated primitives tie exactly; the later leaf wins
+    on both sides, with either device tree."""
+    for reference_tree in (False, True):
+        ids = {}
+        for s in (support.OracleScene(), support.HostSimScene()):
+            if hasattr(s, "set_device_bvh"):
+                s.set_device_bvh(reference_tree)
+            m = s.lambertian_color(0.5, 0.5, 0.5)
+            lst = s.list_create()
+            for i in range(9):
+                s.list_add(lst, s.sphere((0.0, 0.0, -5.0 - (i % 3)), 1.0, m))   # three stacks of identical spheres
+            s.world_add(s.bvh(lst, seed=2))
+            s.commit()
+            rays = np.array([[0, 0, 0, 0, 0, -1, 0], [0.1, 0.2, 0, 0, 0, -1, 0]], np.float32)
+            ids[type(s).__name__] = s.trace_closest(rays)
+        (po, to), (ph, th) = ids["OracleScene"], ids["HostSimScene"]
+        np.testing.assert_array_equal(po, ph)
+        np.testing.assert_array_equal(to, th)
+
+
+def test_edge_rays():
+    """Empty batches, rays that miss everything, rays starting inside a sphere, axis-parallel rays."""
+    o, h = support.OracleScene(), support.HostSimScene()
+    for s in (o, h):
+        scenes.build(s, "random-spheres", seed=1)
+    rays = np.array([[0, 50, 0, 0, 1, 0, 0],            # straight up: miss
+                     [0, 1, 0, 0.3, 0.2, 0.1, 0],       # from the centre of the glass sphere: far root
+                     [13, 2, 3, 0, 0, -1, 0],           # axis-parallel (zero components in the direction)
+                     [0, 0.5, 0, 0, -1, 0, 0]], np.float32)
+    (po, to), (ph, th) = o.trace_closest(rays), h.trace_closest(rays)
+    np.testing.assert_array_equal(po, ph)
+    np.testing.assert_array_equal(to.view(np.uint32), th.view(np.uint32))
+    assert po[0] == -1 and np.isinf(to[0]) and po[1] >= 0
+    p, t = h.trace_closest(np.zeros((0, 7), np.float32))
+    assert len(p) == 0
