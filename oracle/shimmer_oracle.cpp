@@ -956,6 +956,7 @@ using namespace orc;
 #define ORC_API extern "C" __attribute__((visibility("default")))
 
 static thread_local std::string g_err;
+static thread_local Counters g_last;
 static int fail(const std::string& m) { g_err = m; return -1; }
 
 ORC_API const char* orc_last_error() { return g_err.c_str(); }
@@ -1251,7 +1252,13 @@ ORC_API int orc_sample_radiance(void* sp, const float* cam15, const OrcRenderPar
         out_rgb[i * 3] = c.x; out_rgb[i * 3 + 1] = c.y; out_rgb[i * 3 + 2] = c.z;
     }
     if (rays_out) *rays_out = ctx.cnt.rays;
+    g_last = ctx.cnt;
     return 0;
+}
+// counters of the calling thread's last orc_sample_radiance: rays, node visits, prim tests, hrpp tp / fp / none
+ORC_API void orc_last_counters(uint64_t* out6) {
+    out6[0] = g_last.rays; out6[1] = g_last.node_visits; out6[2] = g_last.prim_tests;
+    out6[3] = g_last.hrpp_tp; out6[4] = g_last.hrpp_fp; out6[5] = g_last.hrpp_none;
 }
 
 // Records every ray the integrator traces (camera + bounce rays) for the given samples,

@@ -53,7 +53,16 @@ struct DeviceScene {
     SceneView view;
     SmemLayout smem;
     uint64_t bytes = 0;
-    void release() { if (base) cudaFree(base); base = nullptr; bytes_alloc = 0; }
+    unsigned long long* hrpp_keys = nullptr;  // n_predictors x slots
+    uint32_t* hrpp_leaves = nullptr;           // n_predictors x slots x HRPP_LEAVES
+    size_t hrpp_slots_total = 0;
+    int n_predictors = 0;
+    void release() {
+        if (base) cudaFree(base);
+        if (hrpp_keys) cudaFree(hrpp_keys);
+        if (hrpp_leaves) cudaFree(hrpp_leaves);
+        base = nullptr; hrpp_keys = nullptr; hrpp_leaves = nullptr; bytes_alloc = 0; hrpp_slots_total = 0;
+    }
 };
 
 struct Wavefront {
@@ -163,6 +172,15 @@ SHIM_API int shim_commit(shim_scene* s) {
         v.handle[i] = (const int*)(d.base + o_handle[i]); v.rank[i] = (const int*)(d.base + o_rank[i]); v.leaf[i] = (const int*)(d.base + o_leaf[i]);
     }
     v.n_objects = (int)f.objects.size(); v.n_nodes = (int)f.nodes.size();
+    d.n_predictors = (int)f.predictor_bvh.size();
+    if (d.n_predictors > 0) {  // one open-addressing table per predictor (cleared at the start of every render that uses them)
+        int log2 = 21;
+        if (const char* e = getenv("SHIM_HRPP_LOG2")) { int x = atoi(e); if (x >= 8 && x <= 26) log2 = x; }
+        d.hrpp_slots_total = ((size_t)1 << log2) * (size_t)d.n_predictors;
+        CU(cudaMalloc(&d.hrpp_keys, d.hrpp_slots_total * sizeof(unsigned long long)));
+        CU(cudaMalloc(&d.hrpp_leaves, d.hrpp_slots_total * HRPP_LEAVES * sizeof(uint32_t)));
+        v.hrpp_keys = d.hrpp_keys; v.hrpp_leaves = d.hrpp_leaves; v.hrpp_mask = (uint32_t)(((size_t)1 << log2) - 1); v.hrpp_log2 = log2;
+    }
     d.bytes = f.bytes();
     {   // shared-memory image of what wf_extend walks; total = 0 when it cannot fit any sm_100a block
         SmemLayout& L = d.smem;
@@ -205,12 +223,14 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         w.pool = pool;
         int sms = s->dev->sm_count, per_sm = 0;
         CU(cudaDeviceGetAttribute(&w.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->dev->device));
-        CU(cudaFuncSetAttribute(wf_extend<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         w.grid_extend_smem = sms;  // one persistent block per SM owns the shared-memory copy of the scene
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_extend<false, false, false>, SHIM_EXTEND_THREADS, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_extend<false, false, false, false>, SHIM_EXTEND_THREADS, 0));
         w.grid_extend_gmem = sms * (per_sm > 0 ? per_sm : 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_shade, 256, 0));
         w.grid_shade = sms * (per_sm > 0 ? per_sm : 1);
@@ -232,12 +252,15 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
 }
 
 static void launch_extend(const WfParams& k, int cur, int grid, uint32_t smem, cudaStream_t st) {
-    const bool S = smem != 0, C = k.count_nodes != 0, M = k.has_media != 0;
-#define SHIM_LAUNCH(SS, CC, MM) wf_extend<SS, CC, MM><<<grid, SHIM_EXTEND_THREADS, smem, st>>>(k, cur)
-    if (S) { if (C) { if (M) SHIM_LAUNCH(true, true, true); else SHIM_LAUNCH(true, true, false); }
-             else   { if (M) SHIM_LAUNCH(true, false, true); else SHIM_LAUNCH(true, false, false); } }
-    else   { if (C) { if (M) SHIM_LAUNCH(false, true, true); else SHIM_LAUNCH(false, true, false); }
-             else   { if (M) SHIM_LAUNCH(false, false, true); else SHIM_LAUNCH(false, false, false); } }
+    const bool S = smem != 0, C = k.count_nodes != 0, M = k.has_media != 0, H = k.use_hrpp != 0;
+#define SHIM_LAUNCH(SS, CC, MM, HH) wf_extend<SS, CC, MM, HH><<<grid, SHIM_EXTEND_THREADS, smem, st>>>(k, cur)
+#define SHIM_LAUNCH_M(SS, CC, HH) do { if (M) SHIM_LAUNCH(SS, CC, true, HH); else SHIM_LAUNCH(SS, CC, false, HH); } while (0)
+#define SHIM_LAUNCH_S(CC, HH) do { if (S) SHIM_LAUNCH_M(true, CC, HH); else SHIM_LAUNCH_M(false, CC, HH); } while (0)
+    if (H) SHIM_LAUNCH_S(false, true);       // node counting is not combined with the predictor
+    else if (C) SHIM_LAUNCH_S(true, false);
+    else SHIM_LAUNCH_S(false, false);
+#undef SHIM_LAUNCH_S
+#undef SHIM_LAUNCH_M
 #undef SHIM_LAUNCH
 }
 
@@ -273,6 +296,12 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     k.pool = w.pool; k.width = p.width; k.height = p.height; k.max_depth = p.max_depth; k.sample_begin = p.sample_begin;
     k.bg[0] = p.background[0]; k.bg[1] = p.background[1]; k.bg[2] = p.background[2];
     k.seed = p.seed; k.has_media = s->has_media ? 1 : 0; k.count_nodes = (p.flags & SHIM_RENDER_COUNT_NODES) ? 1 : 0;
+    k.use_hrpp = ((p.flags & SHIM_RENDER_PREDICTORS) && s->dev->scene.n_predictors > 0) ? 1 : 0;
+    if (k.use_hrpp) {  // a fresh Predictor per render (bvh.rs:69-81 builds them with the scene)
+        if (k.count_nodes) return set_err(SHIM_ERR_INVALID, "shim_render: SHIM_RENDER_COUNT_NODES cannot be combined with SHIM_RENDER_PREDICTORS");
+        CU(cudaMemsetAsync(s->dev->scene.hrpp_keys, 0, s->dev->scene.hrpp_slots_total * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(s->dev->scene.hrpp_leaves, 0xFF, s->dev->scene.hrpp_slots_total * HRPP_LEAVES * sizeof(uint32_t), st));
+    }
     k.smem = s->dev->scene.smem;
     const bool use_smem = k.smem.total != 0 && (int)k.smem.total <= w.max_smem - 1024 && !getenv("SHIM_NO_SMEM");
     if (!use_smem) k.smem.total = 0;
@@ -306,7 +335,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
                 launch_extend(k, cur, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
                 if (rec) CU(cudaEventRecord(w.prof[prof_used + 2], st));
                 wf_shade<<<w.grid_shade, 256, 0, st>>>(k, cur);
-                if (k.tail_threshold) wf_tail<<<w.grid_tail, 128, 0, st>>>(k, cur);
+                if (k.tail_threshold) { if (k.use_hrpp) wf_tail<true><<<w.grid_tail, 128, 0, st>>>(k, cur); else wf_tail<false><<<w.grid_tail, 128, 0, st>>>(k, cur); }
                 if (rec) { CU(cudaEventRecord(w.prof[prof_used + 3], st)); prof_used += 4; }
                 launches += k.tail_threshold ? 4 : 3;
                 cur = 1 - cur;
@@ -336,6 +365,9 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         stats->samples = k.total_samples;
         stats->node_visits = c64[C64_NODES];
         stats->prim_tests = c64[C64_PRIMS];
+        stats->hrpp_true_positive = c64[C64_HRPP_TP];
+        stats->hrpp_false_positive = c64[C64_HRPP_FP];
+        stats->hrpp_no_prediction = c64[C64_HRPP_NONE];
         stats->kernel_launches = launches;
         stats->iterations = w.h_flags[32 + CNT_ITER];
         float ms = 0;

@@ -149,7 +149,7 @@ SHIM_HD void make_ctx(RayCtx& c, const Ray& r) {
     c.o_inv = mk3(-(r.o.x * c.inv_d.x), -(r.o.y * c.inv_d.y), -(r.o.z * c.inv_d.z));
 }
 
-struct TraceCounters { uint32_t nodes, prims; };
+struct TraceCounters { uint32_t nodes, prims, hrpp_tp, hrpp_fp, hrpp_none; };
 
 // per-type table lookup with constant indices only, so a SceneView held in registers is never
 // forced into local memory by a dynamic index
@@ -354,8 +354,103 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
     return best.any;
 }
 
-// shape of one top-level object against its object-space ray
+// ---------------------------------------------------------------------------- hrpp.rs:132-193
+SHIM_HD uint32_t hrpp_map_float(float v) {
+    uint32_t bits = (uint32_t)f2i(v);
+    uint32_t sign = (bits >> 31) & 1u, expo = (bits >> 25) & 0x3fu, mant = (bits >> 17) & 0x3fu;
+    return (sign << 15) | (expo << 7) | mant;
+}
+SHIM_HD uint64_t hrpp_hash(const Ray& r) {
+    uint64_t h0 = hrpp_map_float(r.o.x) ^ hrpp_map_float(r.d.z);
+    uint64_t h1 = hrpp_map_float(r.o.y) ^ hrpp_map_float(r.d.y);
+    uint64_t h2 = hrpp_map_float(r.o.z) ^ hrpp_map_float(r.d.x);
+    return h0 | (h1 << 16) | (h2 << 32);
+}
+
+
+// The predictor table (Predictor, hrpp.rs:33-83) as a lock-free open-addressing table.  The reference keeps
+// an unbounded AHashSet of leaf indices per key behind a Mutex; here a slot holds up to HRPP_LEAVES leaves
+// (the cap the reference's own TODO proposes, hrpp.rs:65) and probing is bounded, so an insert into a full
+// neighbourhood is dropped — the table is a cache either way.
+#define SHIM_HRPP_EMPTY 0xFFFFFFFFu
+SHIM_HD unsigned long long hrpp_cas64(unsigned long long* p, unsigned long long expect, unsigned long long val) {
+#if defined(__CUDA_ARCH__)
+    return atomicCAS(p, expect, val);
+#else
+    unsigned long long old = *p; if (old == expect) *p = val; return old;
+#endif
+}
+SHIM_HD uint32_t hrpp_cas32(uint32_t* p, uint32_t expect, uint32_t val) {
+#if defined(__CUDA_ARCH__)
+    return atomicCAS(p, expect, val);
+#else
+    uint32_t old = *p; if (old == expect) *p = val; return old;
+#endif
+}
+SHIM_HD size_t hrpp_home(const SceneView& sv, int table, unsigned long long key) {
+    unsigned long long h = (key * 0x9E3779B97F4A7C15ull) >> (64 - sv.hrpp_log2);
+    return (size_t)table * ((size_t)sv.hrpp_mask + 1) + (size_t)h;
+}
+// Predictor::get_predictions, hrpp.rs:59-62: slot index or -1
+SHIM_HD long long hrpp_lookup(const SceneView& sv, int table, unsigned long long key) {
+    const unsigned long long tag = key | (1ull << 63);
+    size_t base = (size_t)table * ((size_t)sv.hrpp_mask + 1), home = hrpp_home(sv, table, key) - base;
+    for (int p = 0; p < HRPP_PROBES; ++p) {
+        size_t slot = base + ((home + (size_t)p) & sv.hrpp_mask);
+        unsigned long long k = sv.hrpp_keys[slot];
+        if (k == tag) return (long long)slot;
+        if (k == 0ull) return -1;
+    }
+    return -1;
+}
+// Predictor::insert, hrpp.rs:64-82
+SHIM_HD void hrpp_insert(const SceneView& sv, int table, unsigned long long key, uint32_t leaf) {
+    const unsigned long long tag = key | (1ull << 63);
+    size_t base = (size_t)table * ((size_t)sv.hrpp_mask + 1), home = hrpp_home(sv, table, key) - base;
+    for (int p = 0; p < HRPP_PROBES; ++p) {
+        size_t slot = base + ((home + (size_t)p) & sv.hrpp_mask);
+        unsigned long long k = sv.hrpp_keys[slot];
+        if (k == 0ull) k = hrpp_cas64(sv.hrpp_keys + slot, 0ull, tag), k = (k == 0ull) ? tag : k;
+        if (k != tag) continue;
+        uint32_t* l = sv.hrpp_leaves + slot * HRPP_LEAVES;
+        for (int j = 0; j < HRPP_LEAVES; ++j) {
+            uint32_t v = l[j];
+            if (v == SHIM_HRPP_EMPTY) v = hrpp_cas32(l + j, SHIM_HRPP_EMPTY, leaf), v = (v == SHIM_HRPP_EMPTY) ? leaf : v;
+            if (v == leaf) return;
+        }
+        return;  // the slot's leaf list is full
+    }
+}
+
+// Bvh::hit with a predictor, bvh.rs:107-211 (GO_UP_LEVEL = 0: predictions are leaf nodes).  A hit found in the
+// predicted nodes is returned as the answer even if a closer one exists elsewhere (bvh.rs:145-156).
 template <bool COUNT>
+SHIM_HD bool bvh_closest_predicted(const SceneView& sv, const DevObject& ob, const RayCtx& c, float t_min, float t_max, BvhBest& best,
+                                   TraceCounters* cnt) {
+    const unsigned long long key = hrpp_hash(c.r);
+    long long slot = hrpp_lookup(sv, ob.predictor, key);
+    if (slot >= 0) {
+        float closest = t_max;
+        bool any = false;
+        for (int j = 0; j < HRPP_LEAVES; ++j) {
+            uint32_t node = sv.hrpp_leaves[(size_t)slot * HRPP_LEAVES + j];
+            if (node == SHIM_HRPP_EMPTY) break;
+            BvhBest b;
+            if (bvh_closest<COUNT>(sv, (int)node, c, t_min, closest, b, cnt)) { closest = b.t; best = b; any = true; }
+        }
+        if (any) { cnt->hrpp_tp++; return true; }
+        cnt->hrpp_fp++;
+    } else {
+        cnt->hrpp_none++;
+    }
+    if (!bvh_closest<COUNT>(sv, ob.ref, c, t_min, t_max, best, cnt)) return false;
+    int leaf = table_of(sv.leaf, prim_type(best.prim))[prim_index(best.prim)];
+    hrpp_insert(sv, ob.predictor, key, (uint32_t)leaf);
+    return true;
+}
+
+// shape of one top-level object against its object-space ray
+template <bool COUNT, bool HRPP>
 SHIM_HD bool shape_hit(const SceneView& sv, const DevObject& ob, const RayCtx& c, float t_min, float t_max, float& t, uint32_t& prim,
                        int& face, TraceCounters* cnt) {
     if (ob.kind == OBJ_PRIM) {
@@ -365,13 +460,15 @@ SHIM_HD bool shape_hit(const SceneView& sv, const DevObject& ob, const RayCtx& c
         return false;
     }
     BvhBest best;
-    if (bvh_closest<COUNT>(sv, ob.ref, c, t_min, t_max, best, cnt)) { t = best.t; prim = best.prim; face = best.face; return true; }
+    bool hit = (HRPP && (ob.flags & OBJ_PREDICTOR)) ? bvh_closest_predicted<COUNT>(sv, ob, c, t_min, t_max, best, cnt)
+                                                     : bvh_closest<COUNT>(sv, ob.ref, c, t_min, t_max, best, cnt);
+    if (hit) { t = best.t; prim = best.prim; face = best.face; return true; }
     return false;
 }
 
 // HittableList::hit over the flattened world (hittable.rs:100-118), with ConstantMedium::hit
 // (hittable.rs:177-233) for medium objects.  `rng` must be keyed to STAGE_INTERSECT.
-template <bool COUNT>
+template <bool COUNT, bool HRPP = false>
 SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float t_max, Rng& rng, TraceCounters* cnt) {
     Hit h; h.t = t_max; h.obj = -1; h.prim = 0; h.face = 0;
     float closest = t_max;
@@ -382,8 +479,8 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
         float t; uint32_t prim; int face;
         if (ob.flags & OBJ_MEDIUM) {
             float t1, t2;
-            if (!shape_hit<COUNT>(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, cnt)) continue;
-            if (!shape_hit<COUNT>(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, cnt)) continue;
+            if (!shape_hit<COUNT, HRPP>(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, cnt)) continue;
+            if (!shape_hit<COUNT, HRPP>(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, cnt)) continue;
             if (t1 < t_min) t1 = t_min;
             if (t2 > closest) t2 = closest;
             if (t1 >= t2) continue;
@@ -395,7 +492,7 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
             t = t1 + hit_distance / ray_length;
             closest = t;
             h.t = t; h.obj = oi; h.prim = 0; h.face = 0;
-        } else if (shape_hit<COUNT>(sv, ob, c, t_min, closest, t, prim, face, cnt)) {
+        } else if (shape_hit<COUNT, HRPP>(sv, ob, c, t_min, closest, t, prim, face, cnt)) {
             closest = t;
             h.t = t; h.obj = oi; h.prim = prim; h.face = face;
         }
@@ -666,18 +763,5 @@ SHIM_HD bool mat_scatter(const SceneView& sv, int kind, int mi, const Ray& ray, 
 }
 SHIM_HD int mat_kind(const SceneView& sv, int mi) { return f2i(sv.materials[2 * (size_t)mi].x); }
 SHIM_HD bool mat_needs_uv(const SceneView& sv, int mi) { return sv.materials[2 * (size_t)mi + 1].w != 0.0f; }
-
-// ---------------------------------------------------------------------------- hrpp.rs:132-193
-SHIM_HD uint32_t hrpp_map_float(float v) {
-    uint32_t bits = (uint32_t)f2i(v);
-    uint32_t sign = (bits >> 31) & 1u, expo = (bits >> 25) & 0x3fu, mant = (bits >> 17) & 0x3fu;
-    return (sign << 15) | (expo << 7) | mant;
-}
-SHIM_HD uint64_t hrpp_hash(const Ray& r) {
-    uint64_t h0 = hrpp_map_float(r.o.x) ^ hrpp_map_float(r.d.z);
-    uint64_t h1 = hrpp_map_float(r.o.y) ^ hrpp_map_float(r.d.y);
-    uint64_t h2 = hrpp_map_float(r.o.z) ^ hrpp_map_float(r.d.x);
-    return h0 | (h1 << 16) | (h2 << 32);
-}
 
 }  // namespace shim

@@ -30,7 +30,7 @@ namespace shim {
 
 enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..6 */, CNT_TICKET = 8, CNT_DONE = 10, CNT_ITER = 11,
        CNT_U64_BASE = 12 /* u64 slots from here, as pairs */ };
-enum { C64_NEXT_SAMPLE = 0, C64_RAYS = 1, C64_NODES = 2, C64_PRIMS = 3, C64_COUNT = 4 };
+enum { C64_NEXT_SAMPLE = 0, C64_RAYS = 1, C64_NODES = 2, C64_PRIMS = 3, C64_HRPP_TP = 4, C64_HRPP_FP = 5, C64_HRPP_NONE = 6, C64_COUNT = 7 };
 enum { CNT_WORDS = CNT_U64_BASE + 2 * C64_COUNT };
 
 // shared-memory image of the scene arrays wf_extend walks (byte offsets, all multiples of 16)
@@ -60,7 +60,7 @@ struct WfParams {
     int width, height, max_depth, sample_begin;
     float bg[3];
     uint64_t seed;
-    int has_media, count_nodes;
+    int has_media, count_nodes, use_hrpp;
     SmemLayout smem;
 };
 
@@ -157,11 +157,11 @@ __global__ void __launch_bounds__(256) wf_generate(WfParams p, int cur) {
 }
 
 // ---------------------------------------------------------------------------- extend
-template <bool COUNT, bool MEDIA>
+template <bool COUNT, bool MEDIA, bool HRPP>
 __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& sv, int cur, uint32_t n) {
     const uint32_t n_round = (n + 31u) & ~31u;
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t nodes = 0, prims = 0;
+    uint32_t nodes = 0, prims = 0, h_tp = 0, h_fp = 0, h_none = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         int kind = 7;
         f4 o, d, t, hv;
@@ -176,9 +176,9 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
             } else {
                 rng_init(rng, 0, 0, 0);
             }
-            TraceCounters tc; tc.nodes = 0; tc.prims = 0;
-            Hit h = closest_hit<COUNT>(sv, r, 0.001f, SHIM_INF, rng, &tc);
-            nodes += tc.nodes; prims += tc.prims;
+            TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
+            Hit h = closest_hit<COUNT, HRPP>(sv, r, 0.001f, SHIM_INF, rng, &tc);
+            nodes += tc.nodes; prims += tc.prims; h_tp += tc.hrpp_tp; h_fp += tc.hrpp_fp; h_none += tc.hrpp_none;
             if (h.obj < 0) {  // ray.rs:60: miss returns the background
                 if (p.bg[0] != 0.0f || p.bg[1] != 0.0f || p.bg[2] != 0.0f) {
                     float* a = p.accum + 3 * (size_t)(uint32_t)f2i(t.w);
@@ -207,12 +207,24 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
         atomicAdd(cnt64(p.cnt, C64_NODES), (unsigned long long)nodes);
         atomicAdd(cnt64(p.cnt, C64_PRIMS), (unsigned long long)prims);
     }
+    if (HRPP) {  // hrpp.rs:85-130 statistics: one atomic per warp and counter
+        for (int off = 16; off > 0; off >>= 1) {
+            h_tp += __shfl_down_sync(0xffffffffu, h_tp, off);
+            h_fp += __shfl_down_sync(0xffffffffu, h_fp, off);
+            h_none += __shfl_down_sync(0xffffffffu, h_none, off);
+        }
+        if (lane == 0) {
+            if (h_tp) atomicAdd(cnt64(p.cnt, C64_HRPP_TP), (unsigned long long)h_tp);
+            if (h_fp) atomicAdd(cnt64(p.cnt, C64_HRPP_FP), (unsigned long long)h_fp);
+            if (h_none) atomicAdd(cnt64(p.cnt, C64_HRPP_NONE), (unsigned long long)h_none);
+        }
+    }
 }
 
 #ifndef SHIM_EXTEND_THREADS
 #define SHIM_EXTEND_THREADS 768
 #endif
-template <bool SMEM, bool COUNT, bool MEDIA>
+template <bool SMEM, bool COUNT, bool MEDIA, bool HRPP>
 __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend(WfParams p, int cur) {
     const uint32_t n = p.cnt[cur];
     if (blockIdx.x * blockDim.x >= n) return;  // nothing for this block: do not even stage the scene
@@ -242,7 +254,7 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend(WfParams p, 
         sv.objects = reinterpret_cast<const DevObject*>(smem + p.smem.off_objects);
         mbar_wait(&bar, 0);
     }
-    extend_rays<COUNT, MEDIA>(p, sv, cur, n);
+    extend_rays<COUNT, MEDIA, HRPP>(p, sv, cur, n);
 }
 
 // ---------------------------------------------------------------------------- shade
@@ -322,11 +334,13 @@ __global__ void __launch_bounds__(256) wf_shade(WfParams p, int cur) {
 // ---------------------------------------------------------------------------- tail
 // Runs after wf_shade.  When every sample has been started and at most tail_threshold paths are
 // alive, each thread takes one of them and follows it to its end; the queue is then empty.
+template <bool HRPP>
 __global__ void __launch_bounds__(128) wf_tail(WfParams p, int cur) {
     const int nxt = 1 - cur;
     const uint32_t n = p.cnt[nxt];
     if (n == 0 || n > p.tail_threshold || *cnt64(p.cnt, C64_NEXT_SAMPLE) < p.total_samples) return;
     uint32_t traced = 0;
+    TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         f4 o = p.ray_o[nxt][i], d = p.ray_d[nxt][i], t = p.thr[nxt][i];
         uint32_t sample = (uint32_t)f2i(d.w) >> 8, pixel = (uint32_t)f2i(t.w);
@@ -337,7 +351,7 @@ __global__ void __launch_bounds__(128) wf_tail(WfParams p, int cur) {
             rng_init(rng, pixel, sample, p.seed);
             rng_key(rng, (uint32_t)bounce, STAGE_INTERSECT);
             ++traced;
-            Hit h = closest_hit<false>(p.sv, r, 0.001f, SHIM_INF, rng, nullptr);
+            Hit h = closest_hit<false, HRPP>(p.sv, r, 0.001f, SHIM_INF, rng, &tc);
             if (h.obj < 0) {
                 float* a = p.accum + 3 * (size_t)pixel;
                 atomicAdd(a + 0, thr.x * p.bg[0]);
@@ -364,6 +378,11 @@ __global__ void __launch_bounds__(128) wf_tail(WfParams p, int cur) {
     unsigned long long extra = traced;
     for (int off = 16; off > 0; off >>= 1) extra += __shfl_down_sync(0xffffffffu, extra, off);
     if ((threadIdx.x & 31) == 0 && extra) atomicAdd(cnt64(p.cnt, C64_RAYS), extra);
+    if (HRPP) {
+        if (tc.hrpp_tp) atomicAdd(cnt64(p.cnt, C64_HRPP_TP), (unsigned long long)tc.hrpp_tp);
+        if (tc.hrpp_fp) atomicAdd(cnt64(p.cnt, C64_HRPP_FP), (unsigned long long)tc.hrpp_fp);
+        if (tc.hrpp_none) atomicAdd(cnt64(p.cnt, C64_HRPP_NONE), (unsigned long long)tc.hrpp_none);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -388,8 +407,8 @@ __global__ void __launch_bounds__(256) trace_closest_kernel(SceneView sv, const 
         Rng rng;
         rng_init(rng, (uint32_t)i, 0, seed);
         rng_key(rng, 0, STAGE_INTERSECT);
-        TraceCounters tc; tc.nodes = 0; tc.prims = 0;
-        Hit h = counters ? closest_hit<true>(sv, r, t_min, t_max, rng, &tc) : closest_hit<false>(sv, r, t_min, t_max, rng, nullptr);
+        TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
+        Hit h = counters ? closest_hit<true>(sv, r, t_min, t_max, rng, &tc) : closest_hit<false>(sv, r, t_min, t_max, rng, &tc);
         nodes += tc.nodes; prims += tc.prims;
         prim_id[i] = hit_handle(sv, h);
         t_out[i] = h.obj < 0 ? SHIM_INF : h.t;

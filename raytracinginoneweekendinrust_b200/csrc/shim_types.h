@@ -97,7 +97,14 @@ struct SceneView {
     const int* leaf[5];     // device prim index -> node whose child it is (what HRPP stores, bvh.rs:382/398)
     int n_objects;
     int n_nodes;
+    // HRPP predictor tables (hrpp.rs:33-83), one per BVH that carries a predictor: open addressing,
+    // hrpp_mask + 1 slots each; a slot = tagged 48-bit key + up to HRPP_LEAVES predicted leaf nodes
+    unsigned long long* hrpp_keys;
+    uint32_t* hrpp_leaves;
+    uint32_t hrpp_mask;
+    int hrpp_log2;
 };
+enum { HRPP_LEAVES = 4, HRPP_PROBES = 8 };
 
 struct CameraPod {  // camera.rs:6-27, derived on the host by Camera::new
     f3 origin, horizontal, vertical, llc, u, v;

@@ -16,6 +16,41 @@ using namespace shim;
 
 void shim::device_state_release(DeviceState*) {}
 
+// HRPP tables of the harness (the product keeps them in device memory)
+#include <map>
+namespace {
+struct HrppHost { std::vector<unsigned long long> keys; std::vector<uint32_t> leaves; int log2 = 0; bool on = false; uint64_t tp = 0, fp = 0, none = 0; };
+std::map<shim_scene*, HrppHost> g_hrpp;
+SceneView view_of(shim_scene* s) {
+    SceneView sv = s->flat.view();
+    auto it = g_hrpp.find(s);
+    if (it != g_hrpp.end() && it->second.on) {
+        sv.hrpp_keys = it->second.keys.data(); sv.hrpp_leaves = it->second.leaves.data();
+        sv.hrpp_log2 = it->second.log2; sv.hrpp_mask = (uint32_t)(((size_t)1 << it->second.log2) - 1);
+    }
+    return sv;
+}
+bool hrpp_on(shim_scene* s) { auto it = g_hrpp.find(s); return it != g_hrpp.end() && it->second.on; }
+void hrpp_count(shim_scene* s, const TraceCounters& tc) {
+    auto it = g_hrpp.find(s);
+    if (it != g_hrpp.end()) { it->second.tp += tc.hrpp_tp; it->second.fp += tc.hrpp_fp; it->second.none += tc.hrpp_none; }
+}
+}  // namespace
+
+// fresh predictor tables for every BVH recorded with a predictor (2^log2 slots each)
+extern "C" __attribute__((visibility("default"))) int hs_enable_predictors(shim_scene* s, int log2) {
+    HrppHost& h = g_hrpp[s];
+    size_t n = s->flat.predictor_bvh.size();
+    h.log2 = log2; h.on = n > 0; h.tp = h.fp = h.none = 0;
+    h.keys.assign(((size_t)1 << log2) * n, 0ull);
+    h.leaves.assign(((size_t)1 << log2) * n * HRPP_LEAVES, 0xFFFFFFFFu);
+    return (int)n;
+}
+extern "C" __attribute__((visibility("default"))) void hs_predictor_stats(shim_scene* s, uint64_t* out3) {
+    HrppHost& h = g_hrpp[s];
+    out3[0] = h.tp; out3[1] = h.fp; out3[2] = h.none;
+}
+
 extern "C" __attribute__((visibility("default"))) int hs_commit(shim_scene* s);
 // the harness library answers shim_commit with the CPU-side flatten only (no device)
 extern "C" __attribute__((visibility("default"))) int shim_commit(shim_scene* s) { return hs_commit(s); }
@@ -31,7 +66,7 @@ extern "C" __attribute__((visibility("default"))) int hs_commit(shim_scene* s) {
 extern "C" __attribute__((visibility("default"))) int hs_trace_closest(shim_scene* s, const float* rays, int64_t n, float t_min,
                                                                       float t_max, uint64_t seed, int32_t* prim, float* t,
                                                                       uint64_t* counters) {
-    SceneView sv = s->flat.view();
+    SceneView sv = view_of(s);
     uint64_t nodes = 0, prims = 0;
     for (int64_t i = 0; i < n; ++i) {
         const float* q = rays + i * 7;
@@ -39,8 +74,9 @@ extern "C" __attribute__((visibility("default"))) int hs_trace_closest(shim_scen
         Rng rng;
         rng_init(rng, (uint32_t)i, 0, seed);
         rng_key(rng, 0, STAGE_INTERSECT);
-        TraceCounters tc; tc.nodes = 0; tc.prims = 0;
-        Hit h = closest_hit<true>(sv, r, t_min, t_max, rng, &tc);
+        TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
+        Hit h = hrpp_on(s) ? closest_hit<true, true>(sv, r, t_min, t_max, rng, &tc) : closest_hit<true, false>(sv, r, t_min, t_max, rng, &tc);
+        hrpp_count(s, tc);
         nodes += tc.nodes; prims += tc.prims;
         prim[i] = hit_handle(sv, h);
         t[i] = h.obj < 0 ? INFINITY : h.t;
@@ -54,7 +90,7 @@ extern "C" __attribute__((visibility("default"))) int hs_trace_closest(shim_scen
 extern "C" __attribute__((visibility("default"))) int hs_sample_radiance(shim_scene* s, const shim_camera* cam,
                                                                         const shim_render_params* p, const int32_t* xys, int64_t n,
                                                                         float* out_rgb, uint64_t* rays_out) {
-    SceneView sv = s->flat.view();
+    SceneView sv = view_of(s);
     CameraPod c;
     camera_new(cam->look_from, cam->look_at, cam->view_up, cam->vertical_fov, cam->aspect_ratio, cam->aperture, cam->focus_dist,
                cam->time_start, cam->time_end, c);
@@ -71,7 +107,9 @@ extern "C" __attribute__((visibility("default"))) int hs_sample_radiance(shim_sc
             rng_init(rng, pixel, sample, p->seed);
             rng_key(rng, (uint32_t)bounce, STAGE_INTERSECT);
             ++rays;
-            Hit h = closest_hit<false>(sv, r, 0.001f, INFINITY, rng, nullptr);
+            TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
+            Hit h = hrpp_on(s) ? closest_hit<false, true>(sv, r, 0.001f, INFINITY, rng, &tc) : closest_hit<false, false>(sv, r, 0.001f, INFINITY, rng, &tc);
+            hrpp_count(s, tc);
             if (h.obj < 0) { L = L + mk3(thr.x * p->background[0], thr.y * p->background[1], thr.z * p->background[2]); break; }
             int mat = hit_material(sv, h);
             int kind = mat_kind(sv, mat);

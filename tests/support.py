@@ -69,6 +69,8 @@ def oracle_lib():
         lib.orc_sample_radiance.argtypes = [_P, _P, C.POINTER(OrcRenderParams), _P, C.c_int64, _P, _P]
         lib.orc_record_path_rays.restype = C.c_int64
         lib.orc_record_path_rays.argtypes = [_P, _P, C.POINTER(OrcRenderParams), _P, C.c_int64, _P, C.c_int64]
+        lib.orc_last_counters.restype = None
+        lib.orc_last_counters.argtypes = [_P]
         lib.orc_predictor_stats.restype = _I
         lib.orc_predictor_stats.argtypes = [_P, _I, _P, _P]
         _orc = lib
@@ -98,6 +100,10 @@ def hostsim_lib():
         lib.hs_sample_radiance.argtypes = [_P, C.POINTER(Camera), C.POINTER(RenderParams), _P, C.c_int64, _P, _P]
         lib.hs_texture_value.restype = None
         lib.hs_texture_value.argtypes = [_P, _I, _F, _F, _P, _P]
+        lib.hs_enable_predictors.restype = _I
+        lib.hs_enable_predictors.argtypes = [_P, _I]
+        lib.hs_predictor_stats.restype = None
+        lib.hs_predictor_stats.argtypes = [_P, _P]
         lib.hs_philox.restype = None
         lib.hs_philox.argtypes = [_P, _P, _P]
         _hs = lib
@@ -147,6 +153,11 @@ class OracleScene(capi.SceneHandle):
         assert rc == 0
         return out, rays.value
 
+    def last_counters(self):
+        out = np.zeros(6, np.uint64)
+        self.lib.orc_last_counters(out.ctypes.data)
+        return dict(zip(("rays", "node_visits", "prim_tests", "hrpp_tp", "hrpp_fp", "hrpp_none"), (int(v) for v in out)))
+
     def record_path_rays(self, camera: Camera, p: OrcRenderParams, xys, cap):
         xys = np.ascontiguousarray(xys, np.int32).reshape(-1, 3)
         rays = np.zeros((cap, 7), np.float32)
@@ -167,6 +178,14 @@ class HostSimScene(capi.SceneHandle):
         prim = np.empty(n, np.int32); t = np.empty(n, np.float32); cnt = np.zeros(3, np.uint64)
         self.lib.hs_trace_closest(self.ptr, rays.ctypes.data, n, t_min, t_max, seed, prim.ctypes.data, t.ctypes.data, cnt.ctypes.data)
         return (prim, t, cnt) if counters else (prim, t)
+
+    def enable_predictors(self, log2=16):
+        return self.lib.hs_enable_predictors(self.ptr, log2)
+
+    def predictor_stats(self):
+        out = np.zeros(3, np.uint64)
+        self.lib.hs_predictor_stats(self.ptr, out.ctypes.data)
+        return tuple(int(v) for v in out)
 
     def sample_radiance(self, camera: Camera, p: RenderParams, xys):
         xys = np.ascontiguousarray(xys, np.int32).reshape(-1, 3)
