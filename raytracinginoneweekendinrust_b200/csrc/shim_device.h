@@ -41,6 +41,9 @@ SHIM_HD bool signbit_f(float v) { return f2i(v) < 0; }
 
 struct Ray { f3 o, d; float time; };
 SHIM_HD f3 ray_at(const Ray& r, float t) { return r.o + t * r.d; }
+SHIM_HD bool ray_has_nan(const Ray& r) {
+    return (r.o.x != r.o.x) | (r.o.y != r.o.y) | (r.o.z != r.o.z) | (r.d.x != r.d.x) | (r.d.y != r.d.y) | (r.d.z != r.d.z);
+}
 
 // ---------------------------------------------------------------------------- Philox4x32-10
 SHIM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {

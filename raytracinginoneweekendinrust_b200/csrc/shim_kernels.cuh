@@ -168,6 +168,12 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
         if (i < n) {
             o = p.ray_o[cur][i]; d = p.ray_d[cur][i]; t = p.thr[cur][i];
             Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
+            // A ray with a NaN component (born as t = 0/0 in a rect test, rectangle.rs:44, when a ray starts on the
+            // rect's plane with an exactly zero direction component) fails no comparison: in the reference it "hits"
+            // the last object of the world list with t = NaN on every bounce until the depth limit and contributes
+            // nothing, while passing every bounding box on the way.  It is dropped here instead of walking the
+            // whole tree 50 times.
+            const bool poisoned = ray_has_nan(r);
             Rng rng;
             if (MEDIA) {
                 uint32_t bs = (uint32_t)f2i(d.w);
@@ -177,9 +183,12 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
                 rng_init(rng, 0, 0, 0);
             }
             TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
-            Hit h = closest_hit<COUNT, HRPP>(sv, r, 0.001f, SHIM_INF, rng, &tc);
+            Hit h; h.obj = -1; h.t = 0; h.prim = 0; h.face = 0;
+            if (!poisoned) h = closest_hit<COUNT, HRPP>(sv, r, 0.001f, SHIM_INF, rng, &tc);
             nodes += tc.nodes; prims += tc.prims; h_tp += tc.hrpp_tp; h_fp += tc.hrpp_fp; h_none += tc.hrpp_none;
-            if (h.obj < 0) {  // ray.rs:60: miss returns the background
+            if (poisoned) {
+                // path ends without a contribution
+            } else if (h.obj < 0) {  // ray.rs:60: miss returns the background
                 if (p.bg[0] != 0.0f || p.bg[1] != 0.0f || p.bg[2] != 0.0f) {
                     float* a = p.accum + 3 * (size_t)(uint32_t)f2i(t.w);
                     atomicAdd(a + 0, t.x * p.bg[0]);
@@ -351,6 +360,7 @@ __global__ void __launch_bounds__(128) wf_tail(WfParams p, int cur) {
             rng_init(rng, pixel, sample, p.seed);
             rng_key(rng, (uint32_t)bounce, STAGE_INTERSECT);
             ++traced;
+            if (ray_has_nan(r)) break;  // see extend_rays
             Hit h = closest_hit<false, HRPP>(p.sv, r, 0.001f, SHIM_INF, rng, &tc);
             if (h.obj < 0) {
                 float* a = p.accum + 3 * (size_t)pixel;

@@ -107,6 +107,7 @@ extern "C" __attribute__((visibility("default"))) int hs_sample_radiance(shim_sc
             rng_init(rng, pixel, sample, p->seed);
             rng_key(rng, (uint32_t)bounce, STAGE_INTERSECT);
             ++rays;
+            if (ray_has_nan(r)) break;  // as wf_extend: a NaN ray ends the path
             TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
             Hit h = hrpp_on(s) ? closest_hit<false, true>(sv, r, 0.001f, INFINITY, rng, &tc) : closest_hit<false, false>(sv, r, 0.001f, INFINITY, rng, &tc);
             hrpp_count(s, tc);
