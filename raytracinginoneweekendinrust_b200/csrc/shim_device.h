@@ -478,7 +478,8 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
     for (int oi = 0; oi < sv.n_objects; ++oi) {
         const DevObject& ob = sv.objects[oi];
         RayCtx c;
-        make_ctx(c, object_ray(ob, ray));
+        c.r = object_ray(ob, ray);
+        if (ob.kind == OBJ_BVH) make_ctx(c, c.r);  // reciprocals are only needed for box tests
         float t; uint32_t prim; int face;
         if (ob.flags & OBJ_MEDIUM) {
             float t1, t2;
