@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -79,6 +81,9 @@ struct Wavefront {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr};
     int grid_extend_smem = 0, grid_extend_gmem = 0, grid_shade = 0, grid_generate = 0, grid_tail = 0;
     int max_smem = 0;
+    std::mutex render_mutex;                       // one render in flight per device (constant-memory parameters, shared pool)
+    cudaStream_t capture_stream = nullptr;         // graphs are captured here (the caller's stream may be the legacy default stream)
+    std::map<uint64_t, cudaGraphExec_t> graphs;    // one 4-iteration chunk per kernel-variant key
     std::vector<cudaEvent_t> prof;  // event pairs around wf_extend launches (SHIM_RENDER_PROFILE)
     void release() {
         for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); }
@@ -253,7 +258,7 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
 
 static void launch_extend(const WfParams& k, int cur, int grid, uint32_t smem, cudaStream_t st) {
     const bool S = smem != 0, C = k.count_nodes != 0, M = k.has_media != 0, H = k.use_hrpp != 0;
-#define SHIM_LAUNCH(SS, CC, MM, HH) wf_extend<SS, CC, MM, HH><<<grid, SHIM_EXTEND_THREADS, smem, st>>>(k, cur)
+#define SHIM_LAUNCH(SS, CC, MM, HH) wf_extend<SS, CC, MM, HH><<<grid, SHIM_EXTEND_THREADS, smem, st>>>(cur)
 #define SHIM_LAUNCH_M(SS, CC, HH) do { if (M) SHIM_LAUNCH(SS, CC, true, HH); else SHIM_LAUNCH(SS, CC, false, HH); } while (0)
 #define SHIM_LAUNCH_S(CC, HH) do { if (S) SHIM_LAUNCH_M(true, CC, HH); else SHIM_LAUNCH_M(false, CC, HH); } while (0)
     if (H) SHIM_LAUNCH_S(false, true);       // node counting is not combined with the predictor
@@ -262,6 +267,35 @@ static void launch_extend(const WfParams& k, int cur, int grid, uint32_t smem, c
 #undef SHIM_LAUNCH_S
 #undef SHIM_LAUNCH_M
 #undef SHIM_LAUNCH
+}
+
+// one wavefront iteration on `st` (the parameters are already in constant memory)
+static void launch_iteration(const Wavefront& w, const WfParams& k, bool use_smem, int cur, cudaStream_t st) {
+    wf_generate<<<w.grid_generate, 256, 0, st>>>(cur);
+    launch_extend(k, cur, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
+    wf_shade<<<w.grid_shade, 256, 0, st>>>(cur);
+    if (k.tail_threshold) { if (k.use_hrpp) wf_tail<true><<<w.grid_tail, 128, 0, st>>>(cur); else wf_tail<false><<<w.grid_tail, 128, 0, st>>>(cur); }
+}
+
+enum { SHIM_CHUNK = 4 };  // iterations per graph launch / per done-flag readback (even: the queue index pattern repeats)
+
+// the chunk as a CUDA graph, captured once per kernel-variant key on an internal stream
+static int chunk_graph(Wavefront& w, const WfParams& k, bool use_smem, cudaGraphExec_t* out) {
+    uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
+                   ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)(k.tail_threshold != 0) << 35) | ((uint64_t)use_smem << 36);
+    auto it = w.graphs.find(key);
+    if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
+    if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(w.capture_stream, cudaStreamCaptureModeThreadLocal));
+    for (int it2 = 0; it2 < SHIM_CHUNK; ++it2) launch_iteration(w, k, use_smem, it2 & 1, w.capture_stream);
+    CU(cudaStreamEndCapture(w.capture_stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    CU(cudaGraphInstantiate(&exec, graph, 0));
+    CU(cudaGraphDestroy(graph));
+    w.graphs[key] = exec;
+    *out = exec;
+    return SHIM_OK;
 }
 
 SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shim_render_params* pp, float* d_out, shim_stats* stats,
@@ -281,6 +315,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     int rc = wf_prepare(s, p);
     if (rc < 0) return rc;
     Wavefront& w = g_wf[s->dev->device & 63];
+    std::lock_guard<std::mutex> render_lock(w.render_mutex);
 
     WfParams k;
     memset(&k, 0, sizeof k);
@@ -321,25 +356,34 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         w.prof.resize(prof_cap);
         for (size_t i = have; i < prof_cap; ++i) CU(cudaEventCreate(&w.prof[i]));
     }
+    CU(cudaMemcpyToSymbolAsync(g_p, &k, sizeof k, 0, cudaMemcpyHostToDevice, st));
     if (k.total_samples > 0 && p.max_depth > 0) {
-        // iterations are enqueued in chunks; the done flag of chunk c is read back while chunk c+1 runs
-        const int chunk = 4;
-        int cur = 0, pending = -1;
+        // Iterations are enqueued in chunks of SHIM_CHUNK; the done flag of chunk c is read back while chunk c+1
+        // runs.  Without per-kernel events a chunk is one CUDA-graph launch (the loop is launch-bound once the
+        // queue drains: ~80 launches per Book-1 step).
+        const bool use_graph = !profile && !getenv("SHIM_NO_GRAPH");
+        cudaGraphExec_t exec = nullptr;
+        if (use_graph) { int grc = chunk_graph(w, k, use_smem, &exec); if (grc < 0) return grc; }
+        int pending = -1;
         bool done = false;
         for (int c = 0; !done; ++c) {
-            for (int it = 0; it < chunk; ++it) {
-                const bool rec = profile && prof_used + 4 <= prof_cap;
-                if (rec) CU(cudaEventRecord(w.prof[prof_used], st));
-                wf_generate<<<w.grid_generate, 256, 0, st>>>(k, cur);
-                if (rec) CU(cudaEventRecord(w.prof[prof_used + 1], st));
-                launch_extend(k, cur, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
-                if (rec) CU(cudaEventRecord(w.prof[prof_used + 2], st));
-                wf_shade<<<w.grid_shade, 256, 0, st>>>(k, cur);
-                if (k.tail_threshold) { if (k.use_hrpp) wf_tail<true><<<w.grid_tail, 128, 0, st>>>(k, cur); else wf_tail<false><<<w.grid_tail, 128, 0, st>>>(k, cur); }
-                if (rec) { CU(cudaEventRecord(w.prof[prof_used + 3], st)); prof_used += 4; }
-                launches += k.tail_threshold ? 4 : 3;
-                cur = 1 - cur;
+            if (use_graph) {
+                CU(cudaGraphLaunch(exec, st));
+            } else {
+                for (int it = 0; it < SHIM_CHUNK; ++it) {
+                    const int cur = it & 1;
+                    const bool rec = profile && prof_used + 4 <= prof_cap;
+                    if (rec) CU(cudaEventRecord(w.prof[prof_used], st));
+                    wf_generate<<<w.grid_generate, 256, 0, st>>>(cur);
+                    if (rec) CU(cudaEventRecord(w.prof[prof_used + 1], st));
+                    launch_extend(k, cur, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
+                    if (rec) CU(cudaEventRecord(w.prof[prof_used + 2], st));
+                    wf_shade<<<w.grid_shade, 256, 0, st>>>(cur);
+                    if (k.tail_threshold) { if (k.use_hrpp) wf_tail<true><<<w.grid_tail, 128, 0, st>>>(cur); else wf_tail<false><<<w.grid_tail, 128, 0, st>>>(cur); }
+                    if (rec) { CU(cudaEventRecord(w.prof[prof_used + 3], st)); prof_used += 4; }
+                }
             }
+            launches += (uint64_t)SHIM_CHUNK * (k.tail_threshold ? 4 : 3);
             int slot = c & 1;
             CU(cudaMemcpyAsync(w.h_flags + 16 * slot, w.cnt.p + CNT_DONE, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CU(cudaEventRecord(w.ev_chunk[slot], st));

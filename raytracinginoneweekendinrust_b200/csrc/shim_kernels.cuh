@@ -64,6 +64,10 @@ struct WfParams {
     SmemLayout smem;
 };
 
+// The parameters of the render in flight live in constant memory (one render per device at a time), so the
+// wavefront kernels take only the queue index and a 4-iteration chunk can be replayed as one CUDA graph.
+__constant__ WfParams g_p;
+
 __device__ __forceinline__ unsigned long long* cnt64(uint32_t* cnt, int slot) {
     return reinterpret_cast<unsigned long long*>(cnt + CNT_U64_BASE) + slot;
 }
@@ -111,7 +115,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------- generate
 // All blocks read the pre-iteration counters, write their camera rays, and the last block to
 // finish (ticket) publishes the counters the rest of the iteration uses.
-__global__ void __launch_bounds__(256) wf_generate(WfParams p, int cur) {
+__global__ void __launch_bounds__(256) wf_generate(int cur) {
+    const WfParams& p = g_p;
     uint32_t* c = p.cnt;
     const uint32_t n_cur = c[cur];
     const unsigned long long first = *cnt64(c, C64_NEXT_SAMPLE);
@@ -234,7 +239,8 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
 #define SHIM_EXTEND_THREADS 768
 #endif
 template <bool SMEM, bool COUNT, bool MEDIA, bool HRPP>
-__global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend(WfParams p, int cur) {
+__global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend(int cur) {
+    const WfParams& p = g_p;
     const uint32_t n = p.cnt[cur];
     if (blockIdx.x * blockDim.x >= n) return;  // nothing for this block: do not even stage the scene
     SceneView sv = p.sv;
@@ -323,7 +329,8 @@ __device__ __forceinline__ void shade_chunk(const WfParams& p, int cur, uint32_t
 
 // One launch for all material queues: the queues are cut into 256-ray chunks, chunks are dealt
 // round-robin to the persistent blocks, and each chunk runs the code specialised for its material.
-__global__ void __launch_bounds__(256) wf_shade(WfParams p, int cur) {
+__global__ void __launch_bounds__(256) wf_shade(int cur) {
+    const WfParams& p = g_p;
     uint32_t n[MAT_KINDS], first[MAT_KINDS + 1];
     first[0] = 0;
 #pragma unroll
@@ -344,7 +351,8 @@ __global__ void __launch_bounds__(256) wf_shade(WfParams p, int cur) {
 // Runs after wf_shade.  When every sample has been started and at most tail_threshold paths are
 // alive, each thread takes one of them and follows it to its end; the queue is then empty.
 template <bool HRPP>
-__global__ void __launch_bounds__(128) wf_tail(WfParams p, int cur) {
+__global__ void __launch_bounds__(128) wf_tail(int cur) {
+    const WfParams& p = g_p;
     const int nxt = 1 - cur;
     const uint32_t n = p.cnt[nxt];
     if (n == 0 || n > p.tail_threshold || *cnt64(p.cnt, C64_NEXT_SAMPLE) < p.total_samples) return;
