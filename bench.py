@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -286,24 +286,41 @@ def main_gpu(args):
         nodes_per_ray = st_cnt.node_visits / max(1, st_cnt.rays)
         prims_per_ray = st_cnt.prim_tests / max(1, st_cnt.rays)
         prim_bytes = {"random-spheres": 32, "cornell-smoke": 32, "showcase": 32}.get(cfg.scene, 48)
-        bytes_per_ray = nodes_per_ray * 64 + prims_per_ray * prim_bytes + 128
+        # B_ray = N_nodes * node bytes + N_prim * S_prim + B_state.  Only B_state = 128 B/ray (the ray
+        # record read by wf_extend and the ray + hit record it writes to a material queue) has to cross HBM; the node and
+        # primitive bytes are served from the TMA-staged shared-memory image (or L2 for scenes that do not fit).
+        hbm_bytes_per_ray = 128.0
+        onchip_bytes_per_ray = nodes_per_ray * 64 + prims_per_ray * prim_bytes
         ext_ms = sum(s.extend_ms for s in prof_stats)
         ext_launch = sum(s.extend_launches for s in prof_stats)
         rays_rank0 = sum(s.rays for s in prof_stats)
         prof_ms = sum(s.device_ms for s in prof_stats)
         peak, peak_src, sm_max = load_peaks()
-        achieved = bytes_per_ray * rays_rank0 / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
+        achieved = hbm_bytes_per_ray * rays_rank0 / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
         sm_clk = (clocks.get("sm_mhz") or sm_max) * 1e6
         inst_per_ray = nodes_per_ray * 2 * 30 + prims_per_ray * 90 + 150  # SURVEY §8d budget (two boxes per 64 B node, f64 sphere x2)
         issue_peak = 148 * 128 * sm_clk / inst_per_ray / 1e6
+        traffic, traffic_note = None, None
+        tpath = ROOT / "profiles" / "r01_traffic.json"
+        if tpath.exists():
+            tj = json.loads(tpath.read_text())
+            if tj.get("workload") == f"{cfg.key} {W}x{H} {spp}spp":
+                traffic = tj.get("wf_extend_dram_bytes_per_launch")
+                traffic_note = {"captured_launch_rays": tj.get("rays_per_captured_launch"),
+                                "captured_launch_algorithmic_bytes": hbm_bytes_per_ray * tj.get("rays_per_captured_launch", 0),
+                                "source": tj.get("source")}
         roofline = {"bound": "hbm", "kernel": "wf_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "prims_per_ray": prims_per_ray,
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_detail": traffic_note, "peak_source": peak_src,
+                    "algorithmic_bytes_per_ray": hbm_bytes_per_ray,
+                    "algorithmic_bytes_per_launch": hbm_bytes_per_ray * rays_rank0 / max(1, ext_launch),
+                    "onchip_bytes_per_ray": onchip_bytes_per_ray, "nodes_per_ray": nodes_per_ray, "prims_per_ray": prims_per_ray,
+                    "onchip_achieved_gbs": onchip_bytes_per_ray * rays_rank0 / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None,
                     "extend_ms_per_step": ext_ms / max(1, len(prof_stats)), "extend_share_of_step": ext_ms / prof_ms if prof_ms else None,
                     "extend_launches_per_step": ext_launch / max(1, len(prof_stats)),
                     "measured_on": f"{len(prof_stats)} extra steps of the same workload right after the timed steps, CUDA events around every "
-                                   "wf_extend launch (the timed steps carry no per-kernel events)",
-                    "note": "scene data is L1/L2 resident (KB-sized); the binding ceiling is instruction issue, see issue_roofline",
+                                   "wf_extend launch (the timed steps carry no per-kernel events; the event pairs themselves add a few us per launch)",
+                    "note": "HBM is not the binding ceiling of this path (SURVEY.md §8d): nodes and primitives are walked in shared memory and the "
+                            "kernel is limited by instruction issue, see issue_roofline; traffic = ncu dram bytes per launch (profiles/)",
                     "issue_roofline": {"budget_inst_per_ray": inst_per_ray, "sm_mhz": sm_clk / 1e6,
                                        "peak_mrays": issue_peak, "achieved_mrays_extend_only": rays_rank0 / (ext_ms / 1e3) / 1e6 if ext_ms > 0 else None,
                                        "frac": (rays_rank0 / (ext_ms / 1e3) / 1e6) / issue_peak if ext_ms > 0 else None}}
