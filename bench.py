@@ -252,7 +252,7 @@ def main_gpu(args):
     p_e2e = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
                             sample_count=spp, flags=capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0),
                             pool_paths=args.pool)
-    E2E_WARM = 2
+    E2E_WARM = 4
     for k in range(args.e2e_steps + E2E_WARM if args.e2e_steps > 0 else 0):
         s2 = api.Scene()
         scenes.SCENES[cfg.scene](s2, seed=1, **scene_kwargs(cfg, args))  # host-side recording (untimed)
@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--tris", type=int, default=0)
     ap.add_argument("--pool", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--steps-cpu", type=int, default=2)
     ap.add_argument("--warmup-cpu", type=int, default=1)

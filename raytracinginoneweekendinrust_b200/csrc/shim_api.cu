@@ -85,6 +85,7 @@ struct Wavefront {
     cudaStream_t capture_stream = nullptr;         // graphs are captured here (the caller's stream may be the legacy default stream)
     std::map<uint64_t, cudaGraphExec_t> graphs;    // one 4-iteration chunk per kernel-variant key
     std::vector<cudaEvent_t> prof;  // event pairs around wf_extend launches (SHIM_RENDER_PROFILE)
+    std::vector<cudaEvent_t> ev_d2h;
     void release() {
         for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); }
         mq_o.release(); mq_d.release(); mq_thr.release(); mq_hit.release(); cnt.release(); accum.release(); pix_table.release();
@@ -454,9 +455,21 @@ SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_rende
     }
     rc = shim_render_device(s, cam, p, w.d_out.p, stats, nullptr);
     if (rc != SHIM_OK) return rc;
-    CU(cudaMemcpyAsync(w.h_out, w.d_out.p, fb * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
-    CU(cudaStreamSynchronize(nullptr));
-    memcpy(out, w.h_out, fb * sizeof(float));
+    // D2H in chunks through the pinned staging buffer; the copy of chunk k into the caller's (pageable) buffer
+    // overlaps the D2H of the chunks behind it
+    const int chunks = 8;
+    if (w.ev_d2h.empty()) { w.ev_d2h.resize(chunks); for (auto& e : w.ev_d2h) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+    const size_t per = (fb + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; ++c) {
+        size_t off = (size_t)c * per, cnt = off < fb ? (fb - off < per ? fb - off : per) : 0;
+        if (cnt) CU(cudaMemcpyAsync(w.h_out + off, w.d_out.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+        CU(cudaEventRecord(w.ev_d2h[c], nullptr));
+    }
+    for (int c = 0; c < chunks; ++c) {
+        size_t off = (size_t)c * per, cnt = off < fb ? (fb - off < per ? fb - off : per) : 0;
+        CU(cudaEventSynchronize(w.ev_d2h[c]));
+        if (cnt) memcpy(out + off, w.h_out + off, cnt * sizeof(float));
+    }
     return SHIM_OK;
 }
 

@@ -181,6 +181,12 @@ struct SahBuilder {
         return 2.0f * (dx * dy + dy * dz + dz * dx);
     }
     static Box empty() { Box b; for (int k = 0; k < 3; ++k) { b.mn[k] = INFINITY; b.mx[k] = -INFINITY; } return b; }
+    // plain compares (std::fmin / std::fmax are libm calls and dominated the build time)
+    static Box join(const Box& a, const Box& b) {
+        Box r;
+        for (int k = 0; k < 3; ++k) { r.mn[k] = a.mn[k] < b.mn[k] ? a.mn[k] : b.mn[k]; r.mx[k] = a.mx[k] > b.mx[k] ? a.mx[k] : b.mx[k]; }
+        return r;
+    }
     static int ceil_log2(size_t n) { int l = 0; while (((size_t)1 << l) < n) ++l; return l; }
 
     // returns a child reference: >= 0 node index, < 0 ~hittable id
@@ -190,36 +196,37 @@ struct SahBuilder {
         Box bounds = empty(), cb = empty();
         for (size_t i = lo; i < hi; ++i) {
             const Box& b = boxes[idx[i]];
-            bounds = box_union(bounds, b);
+            bounds = join(bounds, b);
             for (int k = 0; k < 3; ++k) {
                 float c = 0.5f * (b.mn[k] + b.mx[k]);
-                cb.mn[k] = std::fmin(cb.mn[k], c); cb.mx[k] = std::fmax(cb.mx[k], c);
+                cb.mn[k] = c < cb.mn[k] ? c : cb.mn[k]; cb.mx[k] = c > cb.mx[k] ? c : cb.mx[k];
             }
         }
         size_t mid = lo + n / 2;
         bool median = depth + ceil_log2(n) >= SHIM_MAX_BVH_HEIGHT - 2;  // keep the height inside the traversal stack
         int best_axis = -1; int best_bin = -1;
-        const int NB = 32;
+        const int NBMAX = 32;
+        const int NB = n <= 8 ? 8 : (n <= 64 ? 16 : NBMAX);   // small nodes dominate the node count: fewer bins there
         if (!median && n > 2) {
             float best_cost = INFINITY;
             for (int axis = 0; axis < 3; ++axis) {
                 float ext = cb.mx[axis] - cb.mn[axis];
                 if (!(ext > 0.0f)) continue;
-                Box bb[NB]; int cnt[NB];
+                Box bb[NBMAX]; int cnt[NBMAX];
                 for (int b = 0; b < NB; ++b) { bb[b] = empty(); cnt[b] = 0; }
                 float scale = (float)NB / ext;
                 for (size_t i = lo; i < hi; ++i) {
                     const Box& bx = boxes[idx[i]];
                     int b = (int)((0.5f * (bx.mn[axis] + bx.mx[axis]) - cb.mn[axis]) * scale);
                     b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-                    bb[b] = box_union(bb[b], bx); cnt[b]++;
+                    bb[b] = join(bb[b], bx); cnt[b]++;
                 }
-                float right_area[NB]; int right_cnt[NB];
+                float right_area[NBMAX]; int right_cnt[NBMAX];
                 Box acc = empty(); int c = 0;
-                for (int b = NB - 1; b > 0; --b) { acc = box_union(acc, bb[b]); c += cnt[b]; right_area[b] = area(acc); right_cnt[b] = c; }
+                for (int b = NB - 1; b > 0; --b) { acc = join(acc, bb[b]); c += cnt[b]; right_area[b] = area(acc); right_cnt[b] = c; }
                 acc = empty(); c = 0;
                 for (int b = 0; b < NB - 1; ++b) {
-                    acc = box_union(acc, bb[b]); c += cnt[b];
+                    acc = join(acc, bb[b]); c += cnt[b];
                     if (c == 0 || right_cnt[b + 1] == 0) continue;
                     float cost = area(acc) * (float)c + right_area[b + 1] * (float)right_cnt[b + 1];
                     if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
@@ -249,7 +256,7 @@ struct SahBuilder {
         Box lb, rb;
         node.left = build(lo, mid, depth + 1, lb);
         node.right = build(mid, hi, depth + 1, rb);
-        node.box = box_union(lb, rb);
+        node.box = join(lb, rb);
         int me = (int)out.size();
         if (node.left >= 0) out[node.left].parent = me;
         if (node.right >= 0) out[node.right].parent = me;
