@@ -236,7 +236,7 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
 }
 
 #ifndef SHIM_EXTEND_THREADS
-#define SHIM_EXTEND_THREADS 768
+#define SHIM_EXTEND_THREADS 640
 #endif
 template <bool SMEM, bool COUNT, bool MEDIA, bool HRPP>
 __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend(int cur) {
