@@ -233,6 +233,10 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         CU(cudaFuncSetAttribute(wf_extend<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_bvh1<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_bvh1<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_bvh1<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_bvh1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         w.grid_extend_smem = sms;  // one persistent block per SM owns the shared-memory copy of the scene
@@ -259,6 +263,12 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
 
 static void launch_extend(const WfParams& k, int cur, int grid, uint32_t smem, cudaStream_t st) {
     const bool S = smem != 0, C = k.count_nodes != 0, M = k.has_media != 0, H = k.use_hrpp != 0;
+    if (k.bvh1_index >= 0) {  // one BVH among plain objects, no medium, no predictor: two-phase variant
+        const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES;
+        if (S) { if (C) wf_extend_bvh1<true, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(cur); else wf_extend_bvh1<true, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(cur); }
+        else   { if (C) wf_extend_bvh1<false, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(cur); else wf_extend_bvh1<false, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(cur); }
+        return;
+    }
 #define SHIM_LAUNCH(SS, CC, MM, HH) wf_extend<SS, CC, MM, HH><<<grid, SHIM_EXTEND_THREADS, smem, st>>>(cur)
 #define SHIM_LAUNCH_M(SS, CC, HH) do { if (M) SHIM_LAUNCH(SS, CC, true, HH); else SHIM_LAUNCH(SS, CC, false, HH); } while (0)
 #define SHIM_LAUNCH_S(CC, HH) do { if (S) SHIM_LAUNCH_M(true, CC, HH); else SHIM_LAUNCH_M(false, CC, HH); } while (0)
@@ -283,7 +293,8 @@ enum { SHIM_CHUNK = 4 };  // iterations per graph launch / per done-flag readbac
 // the chunk as a CUDA graph, captured once per kernel-variant key on an internal stream
 static int chunk_graph(Wavefront& w, const WfParams& k, bool use_smem, cudaGraphExec_t* out) {
     uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
-                   ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)(k.tail_threshold != 0) << 35) | ((uint64_t)use_smem << 36);
+                   ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)(k.tail_threshold != 0) << 35) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
+                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));
@@ -338,8 +349,15 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         CU(cudaMemsetAsync(s->dev->scene.hrpp_keys, 0, s->dev->scene.hrpp_slots_total * sizeof(unsigned long long), st));
         CU(cudaMemsetAsync(s->dev->scene.hrpp_leaves, 0xFF, s->dev->scene.hrpp_slots_total * HRPP_LEAVES * sizeof(uint32_t), st));
     }
+    k.bvh1_index = -1;
+    {   // worlds with exactly one BVH among at least one plain object, no medium, no predictor -> wf_extend_bvh1
+        int n_bvh = 0, idx = -1;
+        for (size_t i = 0; i < s->flat.objects.size(); ++i) if (s->flat.objects[i].kind == OBJ_BVH) { ++n_bvh; idx = (int)i; }
+        if (n_bvh == 1 && s->flat.objects.size() > 1 && !s->has_media && !k.use_hrpp && !getenv("SHIM_NO_BVH1")) k.bvh1_index = idx;
+    }
     k.smem = s->dev->scene.smem;
-    const bool use_smem = k.smem.total != 0 && (int)k.smem.total <= w.max_smem - 1024 && !getenv("SHIM_NO_SMEM");
+    const int smem_extra = k.bvh1_index >= 0 ? SHIM_BVH1_SMEM_BYTES : 0;
+    const bool use_smem = k.smem.total != 0 && (int)k.smem.total + smem_extra <= w.max_smem - 1024 && !getenv("SHIM_NO_SMEM");
     if (!use_smem) k.smem.total = 0;
     k.tail_threshold = 32768;
     if (const char* e = getenv("SHIM_TAIL")) k.tail_threshold = (uint32_t)atoi(e);

@@ -61,6 +61,7 @@ struct WfParams {
     float bg[3];
     uint64_t seed;
     int has_media, count_nodes, use_hrpp;
+    int bvh1_index;   // >= 0: the world is one BVH object (this one) among plain primitives, no medium: wf_extend_bvh1 applies
     SmemLayout smem;
 };
 
@@ -271,6 +272,204 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend(int cur) {
     }
     extend_rays<COUNT, MEDIA, HRPP>(p, sv, cur, n);
 }
+
+// ---------------------------------------------------------------------------- extend, one-BVH worlds
+// Worlds like the reference's mesh scenes (main.rs:791-829): six Cornell rects + Translate(Bvh(triangles)).  Most
+// rays never enter the mesh's bounds, so in the plain kernel a warp idles on the few lanes that walk the tree
+// (measured 9 of 32 lanes active on the bunny config).  Here a warp takes 128 rays at a time.  Phase 1: every lane
+// tests the list objects and the BVH's root boxes for its ray; rays that cannot hit the tree are finished on the
+// spot, the others are compacted (warp ballot) into a shared-memory list.  Phase 2: the list is walked 32 entries
+// at a time, i.e. with dense warps.  List order is kept (hittable.rs:100-118): a later object wins an equal t.
+#define SHIM_BVH1_GROUP 4
+struct Bvh1Entry { uint32_t idx; float closest; int obj_face; uint32_t prim; };   // obj_face: obj | face << 16 | post << 24, obj = 0xffff: none
+
+template <bool COUNT>
+__device__ __forceinline__ void bvh1_finish(const WfParams& p, const SceneView& sv, int cur, uint32_t i, bool valid, bool hit, const Hit& h) {
+    // miss -> background (ray.rs:60); hit -> append ray + hit record to the material queue (one atomic per group)
+    const uint32_t lane = threadIdx.x & 31u;
+    int kind = 7;
+    f4 hv;
+    if (valid) {
+        if (!hit) {
+            if (p.bg[0] != 0.0f || p.bg[1] != 0.0f || p.bg[2] != 0.0f) {
+                f4 t = p.thr[cur][i];
+                float* a = p.accum + 3 * (size_t)(uint32_t)f2i(t.w);
+                atomicAdd(a + 0, t.x * p.bg[0]);
+                atomicAdd(a + 1, t.y * p.bg[1]);
+                atomicAdd(a + 2, t.z * p.bg[2]);
+            }
+        } else {
+            int mat = hit_material(sv, h);
+            kind = mat_kind(sv, mat);
+            hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat);
+        }
+    }
+    unsigned grp = __match_any_sync(0xffffffffu, kind);
+    if (kind < MAT_KINDS) {
+        int leader = __ffs(grp) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(p.cnt + CNT_MQ + kind, (uint32_t)__popc(grp));
+        base = __shfl_sync(grp, base, leader);
+        size_t pos = (size_t)kind * p.pool + base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+        p.mq_o[pos] = p.ray_o[cur][i]; p.mq_d[pos] = p.ray_d[cur][i]; p.mq_thr[pos] = p.thr[cur][i]; p.mq_hit[pos] = hv;
+    }
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void extend_rays_bvh1(const WfParams& p, const SceneView& sv, int cur, uint32_t n, Bvh1Entry* entries_base) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5), warp_global = blockIdx.x * (blockDim.x >> 5) + warp;
+    Bvh1Entry* entries = entries_base + (size_t)warp * (SHIM_BVH1_GROUP * 32);
+    const int bo = p.bvh1_index;
+    const uint32_t group = SHIM_BVH1_GROUP * 32u;
+    TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
+    int stack[SHIM_BVH_STACK];
+    for (uint32_t base = warp_global * group; base < n; base += warps_total * group) {
+        uint32_t count = 0;
+        // ---- phase 1
+        for (uint32_t k = 0; k < SHIM_BVH1_GROUP; ++k) {
+            const uint32_t i = base + k * 32u + lane;
+            bool valid = i < n, need = false, hit = false;
+            Hit h; h.obj = -1; h.t = SHIM_INF; h.prim = 0; h.face = 0;
+            bool post = false;
+            if (valid) {
+                f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i];
+                Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
+                if (ray_has_nan(r)) {
+                    valid = false;   // see extend_rays: the path ends without a contribution
+                } else {
+                    float closest = SHIM_INF;
+                    for (int oi = 0; oi < sv.n_objects; ++oi) {
+                        if (oi == bo) continue;
+                        const DevObject& ob = sv.objects[oi];
+                        RayCtx pc;
+                        pc.r = object_ray(ob, r);
+                        float t; int face = 0;
+                        if (COUNT) tc.prims++;
+                        if (hit_prim(sv, (uint32_t)ob.ref, pc, 0.001f, closest, t, face)) {
+                            closest = t; h.t = t; h.obj = oi; h.prim = (uint32_t)ob.ref; h.face = face; post = oi > bo; hit = true;
+                        }
+                    }
+                    // can the ray reach the tree at all?  (the root's two child boxes, against the closest list hit)
+                    const DevObject& bob = sv.objects[bo];
+                    RayCtx c;
+                    make_ctx(c, object_ray(bob, r));
+                    const DevNode& rn = sv.nodes[bob.ref];
+                    f4 na = rn.a, nb = rn.b, nc = rn.c;
+                    float tl, tr;
+                    need = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, 0.001f, closest, tl) ||
+                           (rn.d.y != CHILD_NONE && slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, 0.001f, closest, tr));
+                }
+            }
+            const unsigned nmask = __ballot_sync(0xffffffffu, need);
+            if (need) {
+                Bvh1Entry e;
+                e.idx = i; e.closest = h.t; e.obj_face = (hit ? h.obj : 0xffff) | (h.face << 16) | ((post ? 1 : 0) << 24); e.prim = h.prim;
+                entries[count + (uint32_t)__popc(nmask & lt_mask)] = e;
+            }
+            count += (uint32_t)__popc(nmask);
+            bvh1_finish<COUNT>(p, sv, cur, i, valid && !need, hit, h);
+        }
+        __syncwarp();
+        // ---- phase 2: dense walks with refill.  Every lane owns one walk; all walks advance "to and through the next
+        // primitive test" together; once half of the lanes have finished (and entries are left), the finished lanes
+        // write their results and take the next entries of the warp's list.
+        uint32_t next = 0;
+        bool active = false, pending = false, hit = false;
+        uint32_t i = 0;
+        Hit h; h.obj = -1; h.t = SHIM_INF; h.prim = 0; h.face = 0;
+        bool post = false;
+        RayCtx c;
+        BvhWalk w;
+        bvh_walk_init(w, 0, 0.0f);
+        w.cur = SHIM_STACK_END;
+        const DevObject& bob = sv.objects[bo];
+        while (count > 0) {
+            if (__any_sync(0xffffffffu, pending)) {
+                if (pending && w.best.any && (!hit || w.best.t < h.t || !post)) {  // an equal t goes to the later list object
+                    h.t = w.best.t; h.obj = bo; h.prim = w.best.prim; h.face = w.best.face; hit = true;
+                }
+                bvh1_finish<COUNT>(p, sv, cur, i, pending, hit, h);
+                pending = false;
+            }
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            const uint32_t left = count - next;
+            if (left > 0 && idle) {
+                const uint32_t my = (uint32_t)__popc(idle & lt_mask);
+                if (!active && my < left) {
+                    const Bvh1Entry en = entries[next + my];
+                    i = en.idx;
+                    const int obj = en.obj_face & 0xffff;
+                    post = ((en.obj_face >> 24) & 1) != 0;
+                    hit = obj != 0xffff;
+                    h.t = en.closest; h.obj = hit ? obj : -1; h.prim = en.prim; h.face = (en.obj_face >> 16) & 0xff;
+                    f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i];
+                    Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
+                    make_ctx(c, object_ray(bob, r));
+                    bvh_walk_init(w, bob.ref, en.closest);
+                    active = true;
+                }
+                const uint32_t n_idle = (uint32_t)__popc(idle);
+                next += n_idle < left ? n_idle : left;
+            }
+            if (!__any_sync(0xffffffffu, active)) break;
+            for (;;) {
+                if (active) {
+                    bvh_walk_step<COUNT>(sv, w, stack, c, 0.001f, &tc);
+                    if (bvh_walk_done(w)) { active = false; pending = true; }
+                }
+                const unsigned act = __ballot_sync(0xffffffffu, active);
+                if (act == 0u) break;
+                if (next < count && __popc(act) <= 16) break;
+            }
+        }
+        if (__any_sync(0xffffffffu, pending)) {
+            if (pending && w.best.any && (!hit || w.best.t < h.t || !post)) { h.t = w.best.t; h.obj = bo; h.prim = w.best.prim; h.face = w.best.face; hit = true; }
+            bvh1_finish<COUNT>(p, sv, cur, i, pending, hit, h);
+            pending = false;
+        }
+        __syncwarp();
+    }
+    if (COUNT) {
+        atomicAdd(cnt64(p.cnt, C64_NODES), (unsigned long long)tc.nodes);
+        atomicAdd(cnt64(p.cnt, C64_PRIMS), (unsigned long long)tc.prims);
+    }
+}
+
+template <bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend_bvh1(int cur) {
+    const WfParams& p = g_p;
+    const uint32_t n = p.cnt[cur];
+    if (blockIdx.x * blockDim.x * SHIM_BVH1_GROUP >= n) return;
+    extern __shared__ __align__(128) unsigned char smem[];   // [scene image (SMEM)] [per-warp entry lists]
+    SceneView sv = p.sv;
+    if (SMEM) {
+        __shared__ uint64_t bar;
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const SmemLayout& L = p.smem;
+            mbar_expect_tx(&bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects);
+            if (L.bytes_nodes) bulk_g2s(smem + L.off_nodes, p.sv.nodes, L.bytes_nodes, &bar);
+            if (L.bytes_sph) bulk_g2s(smem + L.off_sph, p.sv.sph, L.bytes_sph, &bar);
+            if (L.bytes_msph) bulk_g2s(smem + L.off_msph, p.sv.msph, L.bytes_msph, &bar);
+            if (L.bytes_rect) bulk_g2s(smem + L.off_rect, p.sv.rect, L.bytes_rect, &bar);
+            if (L.bytes_tri) bulk_g2s(smem + L.off_tri, p.sv.tri, L.bytes_tri, &bar);
+            if (L.bytes_cube) bulk_g2s(smem + L.off_cube, p.sv.cube, L.bytes_cube, &bar);
+            if (L.bytes_objects) bulk_g2s(smem + L.off_objects, p.sv.objects, L.bytes_objects, &bar);
+        }
+        sv.nodes = reinterpret_cast<const DevNode*>(smem + p.smem.off_nodes);
+        sv.sph = reinterpret_cast<const double*>(smem + p.smem.off_sph);
+        sv.msph = reinterpret_cast<const f4*>(smem + p.smem.off_msph);
+        sv.rect = reinterpret_cast<const f4*>(smem + p.smem.off_rect);
+        sv.tri = reinterpret_cast<const f4*>(smem + p.smem.off_tri);
+        sv.cube = reinterpret_cast<const f4*>(smem + p.smem.off_cube);
+        sv.objects = reinterpret_cast<const DevObject*>(smem + p.smem.off_objects);
+        mbar_wait(&bar, 0);
+    }
+    extend_rays_bvh1<COUNT>(p, sv, cur, n, reinterpret_cast<Bvh1Entry*>(smem + (SMEM ? p.smem.total : 0u)));
+}
+#define SHIM_BVH1_SMEM_BYTES ((SHIM_EXTEND_THREADS / 32) * SHIM_BVH1_GROUP * 32 * (int)sizeof(Bvh1Entry))
 
 // ---------------------------------------------------------------------------- shade
 struct ShadeOut { bool cont; Ray ray; f3 thr; };
