@@ -253,6 +253,7 @@ def main_gpu(args):
                             sample_count=spp, flags=capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0),
                             pool_paths=args.pool)
     E2E_WARM = 4
+    host_fb = np.zeros((H, W, 3), np.float32)   # the caller-owned host framebuffer, reused like a renderer would
     for k in range(args.e2e_steps + E2E_WARM if args.e2e_steps > 0 else 0):
         s2 = api.Scene()
         scenes.SCENES[cfg.scene](s2, seed=1, **scene_kwargs(cfg, args))  # host-side recording (untimed)
@@ -260,7 +261,7 @@ def main_gpu(args):
         t0 = time.perf_counter()
         s2.commit()
         tc = time.perf_counter()
-        _, st2 = s2.render(cfg.camera, p_e2e)
+        _, st2 = s2.render(cfg.camera, p_e2e, out=host_fb)
         dt = time.perf_counter() - t0
         if os.environ.get("BENCH_DEBUG"):
             print(f"e2e step {k}: commit {1e3 * (tc - t0):.2f} ms, render {1e3 * (time.perf_counter() - tc):.2f} ms "

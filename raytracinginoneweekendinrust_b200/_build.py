@@ -15,7 +15,7 @@ HEADERS = ["shim_types.h", "shim_device.h", "shim_kernels.cuh", "shim_scene.h", 
 # -fmad=false / -ffp-contract=off: primitive tests and shading keep the reference's IEEE
 # operation order (see csrc/shim_device.h); sm_100a only.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-shared"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-pthread", "-shared"]
 
 
 def _stale(target: Path, deps) -> bool:

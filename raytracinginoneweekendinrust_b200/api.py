@@ -48,9 +48,12 @@ class Scene(capi.SceneHandle):
         return (prim, t, cnt) if counters else (prim, t)
 
     # ---- render
-    def render(self, camera: Camera, params: RenderParams):
-        """Blocking render into a host framebuffer; returns (H, W, 3) float32 (row 0 = bottom) and Stats."""
-        out = np.empty((params.height, params.width, 3), np.float32)
+    def render(self, camera: Camera, params: RenderParams, out: np.ndarray | None = None):
+        """Blocking render into a host framebuffer; returns (H, W, 3) float32 (row 0 = bottom) and Stats.
+        ``out`` may be a caller-owned C-contiguous float32 array of that shape to be reused across calls."""
+        if out is None:
+            out = np.empty((params.height, params.width, 3), np.float32)
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.shape == (params.height, params.width, 3)
         st = Stats()
         rc = self.lib.shim_render(self.ptr, C.byref(camera), C.byref(params), out.ctypes.data, C.byref(st))
         if rc < 0:
