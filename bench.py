@@ -333,7 +333,7 @@ def main_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(tot_ms.item()) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (+f64 sphere quadratic)", "data": "synthetic",
-                "config": config_dict(cfg, W, H, spp, args, {"sharding": f"sample-range x{world}", "pool_paths": args.pool or (1 << 23),
+                "config": config_dict(cfg, W, H, spp, args, {"sharding": f"sample-range x{world}", "pool_paths": args.pool or (1 << 24),
                                                              "scene_device_bytes": scene.device_bytes()}),
                 "samples_per_s": samples_per_s, "rays_per_step": float(rays.item()) / args.steps,
                 "wall_s_timed_region": wall,

@@ -216,7 +216,7 @@ SHIM_API int shim_commit(shim_scene* s) {
 // ------------------------------------------------------------------------------------------ render
 static int wf_prepare(shim_scene* s, const shim_render_params& p) {
     Wavefront& w = g_wf[s->dev->device & 63];
-    uint32_t pool = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 23);
+    uint32_t pool = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 24);
     const char* env = getenv("SHIM_POOL_PATHS");
     if (p.pool_paths <= 0 && env && atoi(env) > 0) pool = (uint32_t)atoi(env);
     pool = (pool + 31u) & ~31u;
