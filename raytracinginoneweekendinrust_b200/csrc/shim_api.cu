@@ -158,11 +158,12 @@ SHIM_API int shim_commit(shim_scene* s) {
     size_t o_obj = put(f.objects.data(), f.objects.size() * sizeof(DevObject));
     size_t o_mat = put(f.materials.data(), f.materials.size() * 16), o_tex = put(f.textures.data(), f.textures.size() * 16);
     size_t o_img = put(f.images.data(), f.images.size()), o_perlin = put(f.perlin.data(), f.perlin.size());
-    size_t o_handle[5], o_rank[5], o_leaf[5];
+    size_t o_handle[5], o_rank[5], o_leaf[5], o_sib[5];
     for (int i = 0; i < 5; ++i) {
         o_handle[i] = put(f.handle[i].data(), f.handle[i].size() * 4);
         o_rank[i] = put(f.rank[i].data(), f.rank[i].size() * 4);
         o_leaf[i] = put(f.leaf[i].data(), f.leaf[i].size() * 4);
+        o_sib[i] = put(f.sibling[i].data(), f.sibling[i].size() * 4);
     }
     d.release();
     CU(cudaMalloc(&d.base, blob.size()));
@@ -177,6 +178,7 @@ SHIM_API int shim_commit(shim_scene* s) {
     v.images = d.base + o_img; v.perlin = d.base + o_perlin;
     for (int i = 0; i < 5; ++i) {
         v.handle[i] = (const int*)(d.base + o_handle[i]); v.rank[i] = (const int*)(d.base + o_rank[i]); v.leaf[i] = (const int*)(d.base + o_leaf[i]);
+        v.sibling[i] = (const int*)(d.base + o_sib[i]);
     }
     v.n_objects = (int)f.objects.size(); v.n_nodes = (int)f.nodes.size();
     d.n_predictors = (int)f.predictor_bvh.size();

@@ -303,6 +303,18 @@ SHIM_HD bool slab(float mnx, float mny, float mnz, float mxx, float mxy, float m
 struct BvhBest { float t; uint32_t prim; int face; bool any; };
 
 #define SHIM_BVH_STACK 40
+// An exact f32 tie between two primitives of one BVH (bvh.rs:396-415).  Across leaves the reference compares the two
+// f32 t's and the later leaf wins.  Inside one recorded two-primitive leaf it tests the right child against the LEFT
+// child's f32 t, which an f64 sphere root can exceed by the rounding: the right one wins only if it is still a hit
+// under that bound.  Returns whether the candidate replaces the current best.
+SHIM_HD bool tie_goes_to_candidate(const SceneView& sv, const RayCtx& c, float t_min, uint32_t cand, uint32_t best, float t) {
+    const bool later = table_of(sv.rank, prim_type(cand))[prim_index(cand)] > table_of(sv.rank, prim_type(best))[prim_index(best)];
+    if (table_of(sv.sibling, prim_type(cand))[prim_index(cand)] != (int)best) return later;
+    float t2; int f2 = 0;
+    const bool right_survives = hit_prim(sv, later ? cand : best, c, t_min, t, t2, f2);
+    return later ? right_survives : !right_survives;
+}
+
 #define SHIM_STACK_END 0x7fffffff
 template <bool COUNT>
 SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, float t_min, float t_max, BvhBest& best,
@@ -347,8 +359,8 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
             // f32-rounded best.t); what counts is its f32 t: closer wins, an exact tie goes to the later leaf
             // of the recorded tree (bvh.rs:409-415), anything beyond best.t is not a hit
             if (hit_prim(sv, ref, c, t_min, t_cull, t, face) && !(t > best.t)) {
-                bool take = !best.any || t < best.t ||
-                            table_of(sv.rank, prim_type(ref))[prim_index(ref)] > table_of(sv.rank, prim_type(best.prim))[prim_index(best.prim)];
+                bool take = !best.any || t < best.t;
+                if (!take) take = tie_goes_to_candidate(sv, c, t_min, ref, best.prim, t);
                 if (take) { best.t = t; best.prim = ref; best.face = face; best.any = true; t_cull = t + fabsf(t) * 3.8146973e-06f; }
             }
             cur = sp > 0 ? stack[--sp] : SHIM_STACK_END;
@@ -394,8 +406,8 @@ SHIM_HD void bvh_walk_step(const SceneView& sv, BvhWalk& w, int* stack, const Ra
     float t; int face = 0;
     if (COUNT) cnt->prims++;
     if (hit_prim(sv, ref, c, t_min, w.t_cull, t, face) && !(t > w.best.t)) {
-        bool take = !w.best.any || t < w.best.t ||
-                    table_of(sv.rank, prim_type(ref))[prim_index(ref)] > table_of(sv.rank, prim_type(w.best.prim))[prim_index(w.best.prim)];
+        bool take = !w.best.any || t < w.best.t;
+        if (!take) take = tie_goes_to_candidate(sv, c, t_min, ref, w.best.prim, t);
         if (take) { w.best.t = t; w.best.prim = ref; w.best.face = face; w.best.any = true; w.t_cull = t + fabsf(t) * 3.8146973e-06f; }
     }
     w.cur = w.sp > 0 ? stack[--w.sp] : SHIM_STACK_END;

@@ -376,6 +376,7 @@ struct Flattener {
         }
         fs.rank[prim_type(ref)].push_back(0);
         fs.leaf[prim_type(ref)].push_back(-1);
+        fs.sibling[prim_type(ref)].push_back(-1);
         prim_of[hid] = ref;
         return ref;
     }
@@ -402,7 +403,9 @@ struct Flattener {
         if (b.height > SHIM_MAX_BVH_HEIGHT) { fail(SHIM_ERR_UNSUPPORTED_, "BVH taller than the traversal stack"); return -1; }
         // ties (bvh.rs:409-415) go to the primitive that is latest in the left-to-right leaf order of the RECORDED
         // bvh.rs tree, whichever tree the device walks
-        std::unordered_map<int, int> ref_rank;
+        std::unordered_map<int, int> ref_rank, ref_sibling;   // sibling: the other primitive of a recorded two-primitive leaf
+        for (const HostBvhNode& n : rec.nodes)
+            if (n.left < 0 && n.right < 0 && n.left != n.right) { ref_sibling[~n.left] = ~n.right; ref_sibling[~n.right] = ~n.left; }
         {
             int r = 0;
             std::vector<int> st{rec.root};
@@ -414,6 +417,7 @@ struct Flattener {
             }
         }
         bool bad = false;
+        std::vector<std::pair<uint32_t, int>> pending_siblings;   // (prim_ref, sibling hittable id): resolved once every primitive has its ref
         std::function<void(int)> walk = [&](int i) {
             const HostBvhNode& n = b.nodes[i];
             bool dup = n.left < 0 && n.right < 0 && n.left == n.right;
@@ -423,11 +427,17 @@ struct Flattener {
                 uint32_t ref = add_prim(h);
                 fs.rank[prim_type(ref)][prim_index(ref)] = ref_rank[h];
                 fs.leaf[prim_type(ref)][prim_index(ref)] = base + i;
+                auto sb_it = ref_sibling.find(h);
+                if (sb_it != ref_sibling.end()) pending_siblings.push_back({ref, sb_it->second});
             };
             if (n.left >= 0) walk(n.left); else leaf_child(n.left);
             if (n.right >= 0) walk(n.right); else if (!dup) leaf_child(n.right);
         };
         walk(b.root);
+        for (auto& ps : pending_siblings) {
+            auto it = prim_of.find(ps.second);
+            if (it != prim_of.end()) fs.sibling[prim_type(ps.first)][prim_index(ps.first)] = (int)it->second;
+        }
         if (bad) { fail(SHIM_ERR_UNSUPPORTED_, "a BVH may only contain primitives and cubes"); return -1; }
         for (size_t i = 0; i < b.nodes.size(); ++i) {
             const HostBvhNode& n = b.nodes[i];
@@ -553,7 +563,7 @@ SceneView FlatScene::view() const {
     v.msph = msph.data(); v.rect = rect.data(); v.tri = tri.data(); v.cube = cube.data();
     v.objects = objects.data(); v.materials = materials.data(); v.textures = textures.data();
     v.images = images.data(); v.perlin = perlin.data();
-    for (int i = 0; i < 5; ++i) { v.handle[i] = handle[i].data(); v.rank[i] = rank[i].data(); v.leaf[i] = leaf[i].data(); }
+    for (int i = 0; i < 5; ++i) { v.handle[i] = handle[i].data(); v.rank[i] = rank[i].data(); v.leaf[i] = leaf[i].data(); v.sibling[i] = sibling[i].data(); }
     v.n_objects = (int)objects.size(); v.n_nodes = (int)nodes.size();
     return v;
 }
@@ -561,7 +571,7 @@ uint64_t FlatScene::bytes() const {
     uint64_t b = nodes.size() * sizeof(DevNode) + sph.size() * 8 + sph_s.size() * 16 + sph_mat.size() * 4 +
                  (msph.size() + rect.size() + tri.size() + cube.size() + materials.size() + textures.size()) * 16 +
                  objects.size() * sizeof(DevObject) + images.size() + perlin.size();
-    for (int i = 0; i < 5; ++i) b += handle[i].size() * 12;
+    for (int i = 0; i < 5; ++i) b += handle[i].size() * 16;
     return b;
 }
 

@@ -52,7 +52,7 @@ struct FlatScene {
     std::vector<DevObject> objects;
     std::vector<f4> materials, textures;
     std::vector<uint8_t> images, perlin;
-    std::vector<int> handle[5], rank[5], leaf[5];
+    std::vector<int> handle[5], rank[5], leaf[5], sibling[5];
     std::vector<int> predictor_bvh;  // hittable id of each BVH that carries a predictor
     SceneView view() const;          // pointers into the host vectors
     uint64_t bytes() const;

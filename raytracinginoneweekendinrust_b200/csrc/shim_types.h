@@ -95,6 +95,7 @@ struct SceneView {
     const int* handle[5];   // device prim index -> user handle, per PrimType
     const int* rank[5];     // device prim index -> left-to-right leaf rank inside its BVH (ties, bvh.rs:409-415)
     const int* leaf[5];     // device prim index -> node whose child it is (what HRPP stores, bvh.rs:382/398)
+    const int* sibling[5];  // device prim index -> prim_ref of the other primitive of its recorded two-primitive leaf, or -1
     int n_objects;
     int n_nodes;
     // HRPP predictor tables (hrpp.rs:33-83), one per BVH that carries a predictor: open addressing,
