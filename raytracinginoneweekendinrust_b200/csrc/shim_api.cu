@@ -84,7 +84,8 @@ struct Wavefront {
     int max_smem = 0;
     std::mutex render_mutex;                       // one render in flight per device (constant-memory parameters, shared pool)
     cudaStream_t capture_stream = nullptr;         // graphs are captured here (the caller's stream may be the legacy default stream)
-    std::map<uint64_t, cudaGraphExec_t> graphs;    // one 4-iteration chunk per kernel-variant key
+    struct LoopGraph { cudaGraphExec_t exec; unsigned long long handle; };
+    std::map<uint64_t, LoopGraph> graphs;          // the whole wavefront loop as one graph (WHILE node), per kernel-variant key
     std::vector<cudaEvent_t> prof;  // event pairs around wf_extend launches (SHIM_RENDER_PROFILE)
     std::vector<cudaEvent_t> ev_d2h;
     void release() {
@@ -264,15 +265,15 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
     return SHIM_OK;
 }
 
-static void launch_extend(const WfParams& k, int cur, int grid, uint32_t smem, cudaStream_t st) {
+static void launch_extend(const WfParams& k, int grid, uint32_t smem, cudaStream_t st) {
     const bool S = smem != 0, C = k.count_nodes != 0, M = k.has_media != 0, H = k.use_hrpp != 0;
     if (k.bvh1_index >= 0) {  // one BVH among plain objects, no medium, no predictor: two-phase variant
         const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES;
-        if (S) { if (C) wf_extend_bvh1<true, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(cur); else wf_extend_bvh1<true, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(cur); }
-        else   { if (C) wf_extend_bvh1<false, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(cur); else wf_extend_bvh1<false, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(cur); }
+        if (S) { if (C) wf_extend_bvh1<true, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<true, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
+        else   { if (C) wf_extend_bvh1<false, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<false, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
         return;
     }
-#define SHIM_LAUNCH(SS, CC, MM, HH) wf_extend<SS, CC, MM, HH><<<grid, SHIM_EXTEND_THREADS, smem, st>>>(cur)
+#define SHIM_LAUNCH(SS, CC, MM, HH) wf_extend<SS, CC, MM, HH><<<grid, SHIM_EXTEND_THREADS, smem, st>>>()
 #define SHIM_LAUNCH_M(SS, CC, HH) do { if (M) SHIM_LAUNCH(SS, CC, true, HH); else SHIM_LAUNCH(SS, CC, false, HH); } while (0)
 #define SHIM_LAUNCH_S(CC, HH) do { if (S) SHIM_LAUNCH_M(true, CC, HH); else SHIM_LAUNCH_M(false, CC, HH); } while (0)
     if (H) SHIM_LAUNCH_S(false, true);       // node counting is not combined with the predictor
@@ -283,33 +284,50 @@ static void launch_extend(const WfParams& k, int cur, int grid, uint32_t smem, c
 #undef SHIM_LAUNCH
 }
 
-// one wavefront iteration on `st` (the parameters are already in constant memory)
-static void launch_iteration(const Wavefront& w, const WfParams& k, bool use_smem, int cur, cudaStream_t st) {
-    wf_generate<<<w.grid_generate, 256, 0, st>>>(cur);
-    launch_extend(k, cur, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
-    wf_shade<<<w.grid_shade, 256, 0, st>>>(cur);
-    if (k.tail_threshold) { if (k.use_hrpp) wf_tail<true><<<w.grid_tail, 128, 0, st>>>(cur); else wf_tail<false><<<w.grid_tail, 128, 0, st>>>(cur); }
+// one wavefront iteration on `st` (the parameters are already in constant memory, the queue index in the counters)
+static void launch_tail(const Wavefront& w, const WfParams& k, cudaStream_t st) {
+    if (k.use_hrpp) wf_tail<true><<<w.grid_tail, 128, 0, st>>>(); else wf_tail<false><<<w.grid_tail, 128, 0, st>>>();
+}
+static void launch_iteration(const Wavefront& w, const WfParams& k, bool use_smem, cudaStream_t st) {
+    wf_generate<<<w.grid_generate, 256, 0, st>>>();
+    launch_extend(k, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
+    wf_shade<<<w.grid_shade, 256, 0, st>>>();
+    launch_tail(w, k, st);   // also the loop's condition: done flag / WHILE-node condition
 }
 
-enum { SHIM_CHUNK = 4 };  // iterations per graph launch / per done-flag readback (even: the queue index pattern repeats)
+// The whole loop as one CUDA graph: a WHILE conditional node whose body is one iteration; wf_tail sets the condition
+// on the device, so a render is one graph launch and the host never polls.  Built once per kernel-variant key on an
+// internal stream.
+enum { SHIM_CHUNK = 4 };  // iterations per done-flag readback of the host-driven loop
 
-// the chunk as a CUDA graph, captured once per kernel-variant key on an internal stream
-static int chunk_graph(Wavefront& w, const WfParams& k, bool use_smem, cudaGraphExec_t* out) {
+static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
     uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
-                   ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)(k.tail_threshold != 0) << 35) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
+                   ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
                    ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
-    CU(cudaStreamBeginCapture(w.capture_stream, cudaStreamCaptureModeThreadLocal));
-    for (int it2 = 0; it2 < SHIM_CHUNK; ++it2) launch_iteration(w, k, use_smem, it2 & 1, w.capture_stream);
-    CU(cudaStreamEndCapture(w.capture_stream, &graph));
+    CU(cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle handle;
+    CU(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    CU(cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    CU(cudaStreamBeginCaptureToGraph(w.capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    launch_iteration(w, k, use_smem, w.capture_stream);
+    CU(cudaStreamEndCapture(w.capture_stream, nullptr));
     cudaGraphExec_t exec = nullptr;
     CU(cudaGraphInstantiate(&exec, graph, 0));
     CU(cudaGraphDestroy(graph));
-    w.graphs[key] = exec;
-    *out = exec;
+    Wavefront::LoopGraph lg{exec, (unsigned long long)handle};
+    w.graphs[key] = lg;
+    *out = lg;
     return SHIM_OK;
 }
 
@@ -363,7 +381,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     {   // worlds with exactly one BVH among at least one plain object, no medium, no predictor -> wf_extend_bvh1
         int n_bvh = 0, idx = -1;
         for (size_t i = 0; i < s->flat.objects.size(); ++i) if (s->flat.objects[i].kind == OBJ_BVH) { ++n_bvh; idx = (int)i; }
-        if (n_bvh == 1 && s->flat.objects.size() > 1 && !s->has_media && !k.use_hrpp && !getenv("SHIM_NO_BVH1")) k.bvh1_index = idx;
+        if (n_bvh == 1 && (s->flat.objects.size() > 1 || getenv("SHIM_FORCE_BVH1")) && !s->has_media && !k.use_hrpp && !getenv("SHIM_NO_BVH1")) k.bvh1_index = idx;
     }
     k.smem = s->dev->scene.smem;
     const int smem_extra = k.bvh1_index >= 0 ? SHIM_BVH1_SMEM_BYTES : 0;
@@ -376,7 +394,6 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     CU(cudaMemsetAsync(w.accum.p, 0, w.accum.n * sizeof(float), st));
     CU(cudaEventRecord(w.ev0, st));
 
-    uint64_t launches = 0;
     const bool profile = (p.flags & SHIM_RENDER_PROFILE) != 0;
     size_t prof_used = 0;
     const size_t prof_cap = 4 * 1024;
@@ -385,34 +402,33 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         w.prof.resize(prof_cap);
         for (size_t i = have; i < prof_cap; ++i) CU(cudaEventCreate(&w.prof[i]));
     }
+    k.max_iterations = 1u << 30;
+    const bool run = k.total_samples > 0 && p.max_depth > 0;
+    // Without per-kernel events the loop is ONE graph launch (WHILE node, condition set by wf_tail on the device).
+    const bool use_graph = run && !profile && !getenv("SHIM_NO_GRAPH");
+    Wavefront::LoopGraph lg{nullptr, 0ull};
+    if (use_graph) { int grc = loop_graph(w, k, use_smem, &lg); if (grc < 0) return grc; }
+    k.loop_handle = lg.handle;
     CU(cudaMemcpyToSymbolAsync(g_p, &k, sizeof k, 0, cudaMemcpyHostToDevice, st));
-    if (k.total_samples > 0 && p.max_depth > 0) {
-        // Iterations are enqueued in chunks of SHIM_CHUNK; the done flag of chunk c is read back while chunk c+1
-        // runs.  Without per-kernel events a chunk is one CUDA-graph launch (the loop is launch-bound once the
-        // queue drains: ~80 launches per Book-1 step).
-        const bool use_graph = !profile && !getenv("SHIM_NO_GRAPH");
-        cudaGraphExec_t exec = nullptr;
-        if (use_graph) { int grc = chunk_graph(w, k, use_smem, &exec); if (grc < 0) return grc; }
+    if (use_graph) {
+        CU(cudaGraphLaunch(lg.exec, st));
+    } else if (run) {
+        // host-driven loop (profiling pass: CUDA events around every kernel): iterations are enqueued in chunks and the
+        // done flag of chunk c is read back while chunk c+1 runs
         int pending = -1;
         bool done = false;
         for (int c = 0; !done; ++c) {
-            if (use_graph) {
-                CU(cudaGraphLaunch(exec, st));
-            } else {
-                for (int it = 0; it < SHIM_CHUNK; ++it) {
-                    const int cur = it & 1;
-                    const bool rec = profile && prof_used + 4 <= prof_cap;
-                    if (rec) CU(cudaEventRecord(w.prof[prof_used], st));
-                    wf_generate<<<w.grid_generate, 256, 0, st>>>(cur);
-                    if (rec) CU(cudaEventRecord(w.prof[prof_used + 1], st));
-                    launch_extend(k, cur, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
-                    if (rec) CU(cudaEventRecord(w.prof[prof_used + 2], st));
-                    wf_shade<<<w.grid_shade, 256, 0, st>>>(cur);
-                    if (k.tail_threshold) { if (k.use_hrpp) wf_tail<true><<<w.grid_tail, 128, 0, st>>>(cur); else wf_tail<false><<<w.grid_tail, 128, 0, st>>>(cur); }
-                    if (rec) { CU(cudaEventRecord(w.prof[prof_used + 3], st)); prof_used += 4; }
-                }
+            for (int it = 0; it < SHIM_CHUNK; ++it) {
+                const bool rec = profile && prof_used + 4 <= prof_cap;
+                if (rec) CU(cudaEventRecord(w.prof[prof_used], st));
+                wf_generate<<<w.grid_generate, 256, 0, st>>>();
+                if (rec) CU(cudaEventRecord(w.prof[prof_used + 1], st));
+                launch_extend(k, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
+                if (rec) CU(cudaEventRecord(w.prof[prof_used + 2], st));
+                wf_shade<<<w.grid_shade, 256, 0, st>>>();
+                launch_tail(w, k, st);
+                if (rec) { CU(cudaEventRecord(w.prof[prof_used + 3], st)); prof_used += 4; }
             }
-            launches += (uint64_t)SHIM_CHUNK * (k.tail_threshold ? 4 : 3);
             int slot = c & 1;
             CU(cudaMemcpyAsync(w.h_flags + 16 * slot, w.cnt.p + CNT_DONE, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CU(cudaEventRecord(w.ev_chunk[slot], st));
@@ -426,7 +442,6 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     }
     size_t fb = (size_t)p.width * p.height * 3;
     wf_finalize<<<s->dev->sm_count * 4, 256, 0, st>>>(w.accum.p, d_out, fb, (float)p.samples_per_pixel, (p.flags & SHIM_RENDER_RAW_SUM) ? 1 : 0);
-    launches += 1;
     CU(cudaEventRecord(w.ev1, st));
     CU(cudaMemcpyAsync(w.h_flags + 32, w.cnt.p, CNT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -441,8 +456,9 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         stats->hrpp_true_positive = c64[C64_HRPP_TP];
         stats->hrpp_false_positive = c64[C64_HRPP_FP];
         stats->hrpp_no_prediction = c64[C64_HRPP_NONE];
-        stats->kernel_launches = launches;
         stats->iterations = w.h_flags[32 + CNT_ITER];
+        // four kernels per executed iteration body (the last body may find the queue already empty) + wf_finalize
+        stats->kernel_launches = 4ull * w.h_flags[32 + CNT_BODIES] + 1ull;
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
         stats->device_ms = ms;

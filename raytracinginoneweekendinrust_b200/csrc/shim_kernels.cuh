@@ -28,8 +28,8 @@
 
 namespace shim {
 
-enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..6 */, CNT_TICKET = 8, CNT_DONE = 10, CNT_ITER = 11,
-       CNT_U64_BASE = 12 /* u64 slots from here, as pairs */ };
+enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..6 */, CNT_CUR = 7, CNT_TICKET = 8, CNT_NEXT_CUR = 9, CNT_DONE = 10, CNT_ITER = 11,
+       CNT_BODIES = 12 /* iteration bodies executed */, CNT_U64_BASE = 14 /* u64 slots from here, as pairs */ };
 enum { C64_NEXT_SAMPLE = 0, C64_RAYS = 1, C64_NODES = 2, C64_PRIMS = 3, C64_HRPP_TP = 4, C64_HRPP_FP = 5, C64_HRPP_NONE = 6, C64_COUNT = 7 };
 enum { CNT_WORDS = CNT_U64_BASE + 2 * C64_COUNT };
 
@@ -63,10 +63,13 @@ struct WfParams {
     int has_media, count_nodes, use_hrpp;
     int bvh1_index;   // >= 0: the world is one BVH object (this one) among plain primitives, no medium: wf_extend_bvh1 applies
     SmemLayout smem;
+    unsigned long long loop_handle;   // conditional handle of the CUDA-graph WHILE node the iteration runs in (0: host-driven loop)
+    uint32_t max_iterations;          // safety stop of the device-side loop
 };
 
-// The parameters of the render in flight live in constant memory (one render per device at a time), so the
-// wavefront kernels take only the queue index and a 4-iteration chunk can be replayed as one CUDA graph.
+// The parameters of the render in flight live in constant memory (one render per device at a time) and the index of
+// the current ray queue lives in the counters (wf_generate's last block flips it), so the wavefront kernels take no
+// arguments: one iteration is the body of a CUDA-graph WHILE node whose condition wf_tail sets on the device.
 __constant__ WfParams g_p;
 
 __device__ __forceinline__ unsigned long long* cnt64(uint32_t* cnt, int slot) {
@@ -116,9 +119,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------- generate
 // All blocks read the pre-iteration counters, write their camera rays, and the last block to
 // finish (ticket) publishes the counters the rest of the iteration uses.
-__global__ void __launch_bounds__(256) wf_generate(int cur) {
+__global__ void __launch_bounds__(256) wf_generate() {
     const WfParams& p = g_p;
     uint32_t* c = p.cnt;
+    const int cur = (int)c[CNT_NEXT_CUR];
     const uint32_t n_cur = c[cur];
     const unsigned long long first = *cnt64(c, C64_NEXT_SAMPLE);
     const unsigned long long remaining = p.total_samples - first;
@@ -149,14 +153,16 @@ __global__ void __launch_bounds__(256) wf_generate(int cur) {
         uint32_t ticket = atomicAdd(c + CNT_TICKET, 1u);
         if (ticket == gridDim.x - 1) {  // every block has read the old counters: publish the new ones
             c[CNT_TICKET] = 0;
+            c[CNT_CUR] = (uint32_t)cur;            // the queue the rest of this iteration works on
+            c[CNT_NEXT_CUR] = (uint32_t)(1 - cur);
             *cnt64(c, C64_NEXT_SAMPLE) = first + n;
             c[cur] = n_cur + n;
             c[1 - cur] = 0;
 #pragma unroll
             for (int k = 0; k < MAT_KINDS; ++k) c[CNT_MQ + k] = 0;
             *cnt64(c, C64_RAYS) += (unsigned long long)(n_cur + n);
-            c[CNT_DONE] = (n_cur + n == 0) ? 1u : 0u;
             c[CNT_ITER] += (n_cur + n == 0) ? 0u : 1u;
+            c[CNT_BODIES] += 1u;
             __threadfence();
         }
     }
@@ -240,8 +246,9 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
 #define SHIM_EXTEND_THREADS 640
 #endif
 template <bool SMEM, bool COUNT, bool MEDIA, bool HRPP>
-__global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend(int cur) {
+__global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
     const WfParams& p = g_p;
+    const int cur = (int)p.cnt[CNT_CUR];
     const uint32_t n = p.cnt[cur];
     if (blockIdx.x * blockDim.x >= n) return;  // nothing for this block: do not even stage the scene
     SceneView sv = p.sv;
@@ -437,8 +444,9 @@ __device__ __forceinline__ void extend_rays_bvh1(const WfParams& p, const SceneV
 }
 
 template <bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend_bvh1(int cur) {
+__global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend_bvh1() {
     const WfParams& p = g_p;
+    const int cur = (int)p.cnt[CNT_CUR];
     const uint32_t n = p.cnt[cur];
     if (blockIdx.x * blockDim.x * SHIM_BVH1_GROUP >= n) return;
     extern __shared__ __align__(128) unsigned char smem[];   // [scene image (SMEM)] [per-warp entry lists]
@@ -528,8 +536,9 @@ __device__ __forceinline__ void shade_chunk(const WfParams& p, int cur, uint32_t
 
 // One launch for all material queues: the queues are cut into 256-ray chunks, chunks are dealt
 // round-robin to the persistent blocks, and each chunk runs the code specialised for its material.
-__global__ void __launch_bounds__(256) wf_shade(int cur) {
+__global__ void __launch_bounds__(256) wf_shade() {
     const WfParams& p = g_p;
+    const int cur = (int)p.cnt[CNT_CUR];
     uint32_t n[MAT_KINDS], first[MAT_KINDS + 1];
     first[0] = 0;
 #pragma unroll
@@ -549,12 +558,24 @@ __global__ void __launch_bounds__(256) wf_shade(int cur) {
 // ---------------------------------------------------------------------------- tail
 // Runs after wf_shade.  When every sample has been started and at most tail_threshold paths are
 // alive, each thread takes one of them and follows it to its end; the queue is then empty.
+// It is also where the loop ends: the render is done when the next queue is empty and every sample has been started;
+// that sets the done flag and, when the iteration runs inside a CUDA-graph WHILE node, the node's condition.
+__device__ __forceinline__ void loop_publish(const WfParams& p, bool done) {
+    if (p.cnt[CNT_ITER] >= p.max_iterations) done = true;
+    p.cnt[CNT_DONE] = done ? 1u : 0u;
+    if (p.loop_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)p.loop_handle, done ? 0u : 1u);
+}
 template <bool HRPP>
-__global__ void __launch_bounds__(128) wf_tail(int cur) {
+__global__ void __launch_bounds__(128) wf_tail() {
     const WfParams& p = g_p;
+    const int cur = (int)p.cnt[CNT_CUR];
     const int nxt = 1 - cur;
     const uint32_t n = p.cnt[nxt];
-    if (n == 0 || n > p.tail_threshold || *cnt64(p.cnt, C64_NEXT_SAMPLE) < p.total_samples) return;
+    const bool all_started = *cnt64(p.cnt, C64_NEXT_SAMPLE) >= p.total_samples;
+    if (n == 0 || n > p.tail_threshold || !all_started) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) loop_publish(p, n == 0 && all_started);
+        return;
+    }
     uint32_t traced = 0;
     TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -604,7 +625,7 @@ __global__ void __launch_bounds__(128) wf_tail(int cur) {
     if (threadIdx.x == 0) {
         __threadfence();
         uint32_t ticket = atomicAdd(p.cnt + CNT_TICKET, 1u);
-        if (ticket == gridDim.x - 1) { p.cnt[CNT_TICKET] = 0; p.cnt[nxt] = 0; __threadfence(); }
+        if (ticket == gridDim.x - 1) { p.cnt[CNT_TICKET] = 0; p.cnt[nxt] = 0; loop_publish(p, true); __threadfence(); }
     }
 }
 
