@@ -253,7 +253,9 @@ def main_gpu(args):
                             sample_count=spp, flags=capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0),
                             pool_paths=args.pool)
     E2E_WARM = 4
-    host_fb = np.zeros((H, W, 3), np.float32)   # the caller-owned host framebuffer, reused like a renderer would
+    # the caller-owned host framebuffer, reused like a renderer would: page-locked (shim_host_alloc) unless --pageable-fb
+    pinned_fb = None if args.pageable_fb else api.HostFramebuffer(H, W)
+    host_fb = np.zeros((H, W, 3), np.float32) if pinned_fb is None else pinned_fb.array
     for k in range(args.e2e_steps + E2E_WARM if args.e2e_steps > 0 else 0):
         s2 = api.Scene()
         scenes.SCENES[cfg.scene](s2, seed=1, **scene_kwargs(cfg, args))  # host-side recording (untimed)
@@ -269,7 +271,7 @@ def main_gpu(args):
         if k >= E2E_WARM:  # the first ones warm the pinned staging buffer / allocator
             e2e_ms.append(dt * 1e3)
             e2e_rays += st2.rays
-        h2d = s2.device_bytes() + W * H * 4
+        h2d = s2.device_bytes()   # the scene blob; the tile-ordered pixel table is cached on the device after the first render
         s2.close()
     e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     e2e_r = torch.tensor([float(e2e_rays)], dtype=torch.float64, device=dev)
@@ -340,7 +342,8 @@ def main_gpu(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": float(e2e_t.item()) / max(1, len(e2e_ms)),
-                        "what": "shim_commit (flatten + scene H2D) + shim_render into a host framebuffer (D2H), host timer"},
+                        "what": "shim_commit (flatten + scene H2D) + shim_render into a host framebuffer (D2H), host timer",
+                        "host_framebuffer": "pageable" if args.pageable_fb else "page-locked (shim_host_alloc)"},
                 "gpu_launches": int(sum(s.kernel_launches for s in stats)),
                 "iterations_per_step": float(np.mean([s.iterations for s in stats])),
                 "roofline": roofline, "cpu_baseline": cpu}
@@ -362,6 +365,7 @@ def main():
     ap.add_argument("--tris", type=int, default=0)
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--pageable-fb", action="store_true", help="e2e: ordinary (pageable) host framebuffer instead of shim_host_alloc")
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--steps-cpu", type=int, default=2)
     ap.add_argument("--warmup-cpu", type=int, default=1)

@@ -143,6 +143,11 @@ typedef struct shim_stats {
 /* host framebuffer: width*height*3 floats, linear radiance, row-major, y = 0 is the bottom row
  * (ImageColors, renderer.rs:168-194) */
 int shim_render(shim_scene* s, const shim_camera* cam, const shim_render_params* p, float* out_rgb, shim_stats* stats);
+/* Page-locked host memory for the framebuffer a renderer reuses across calls (the Vec behind ImageColors,
+ * renderer.rs:168-194).  shim_render copies straight into a buffer obtained here (one D2H, no staging);
+ * any other host pointer works too and goes through the library's pinned staging buffer.  Needs a CUDA device. */
+float* shim_host_alloc(size_t floats);
+void shim_host_free(float* p);
 /* same, into a device buffer of the current device on `cuda_stream` (0 = default stream) */
 int shim_render_device(shim_scene* s, const shim_camera* cam, const shim_render_params* p, float* d_out_rgb,
                        shim_stats* stats, void* cuda_stream);

@@ -70,6 +70,31 @@ class Scene(capi.SceneHandle):
         return st
 
 
+class HostFramebuffer:
+    """A page-locked (H, W, 3) float32 framebuffer from ``shim_host_alloc``: ``Scene.render(..., out=fb.array)`` copies
+    device -> host straight into it.  Free with ``close()`` (or let it be collected)."""
+
+    def __init__(self, height: int, width: int):
+        self.lib = capi.load_library()
+        n = height * width * 3
+        self.ptr = self.lib.shim_host_alloc(n)
+        if not self.ptr:
+            raise ShimError(-1, self.lib.shim_last_error().decode())
+        self.array = np.ctypeslib.as_array((C.c_float * n).from_address(self.ptr)).reshape(height, width, 3)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self.lib.shim_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def make_params(width, height, spp, max_depth=50, tile_width=8, tile_height=8, background=(0.0, 0.0, 0.0), seed=0,
                 sample_begin=0, sample_count=0, tile_rank=0, tile_world=0, flags=0, pool_paths=0) -> RenderParams:
     p = RenderParams()

@@ -166,6 +166,10 @@ def load_library() -> C.CDLL:
     lib.shim_camera_fields.argtypes = [C.POINTER(Camera), _P]
     lib.shim_hrpp_hash.restype = C.c_uint64
     lib.shim_hrpp_hash.argtypes = [_P, _P]
+    lib.shim_host_alloc.restype = _P
+    lib.shim_host_alloc.argtypes = [C.c_size_t]
+    lib.shim_host_free.restype = None
+    lib.shim_host_free.argtypes = [_P]
     lib.shim_write_ppm.restype = C.c_int64
     lib.shim_write_ppm.argtypes = [_P, _I, _I, C.c_char_p]
     _lib = lib

@@ -2,6 +2,7 @@
 // wavefront driver and the gate-1 batch query.  No CPU fallback: every device entry point
 // fails with SHIM_ERR_CUDA when no CUDA device is usable.
 #include <cuda_runtime.h>
+#include <chrono>
 
 #include <cmath>
 #include <cstdio>
@@ -137,8 +138,17 @@ static int ensure_device(shim_scene* s) {
 
 SHIM_API int shim_commit(shim_scene* s) {
     MUTABLE(s);
+    const bool trace_commit = getenv("SHIM_TRACE_COMMIT") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace_commit) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "shim-commit %s %.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_start).count());
+        t_start = now;
+    };
     int rc = s->sb.flatten(s->flat);
     if (rc < 0) return set_err(rc, s->sb.err);
+    lap("flatten");
     if (s->flat.objects.size() > 65535) return set_err(SHIM_ERR_UNSUPPORTED, "more than 65535 top-level objects");
     rc = ensure_device(s);
     if (rc < 0) return rc;
@@ -166,10 +176,13 @@ SHIM_API int shim_commit(shim_scene* s) {
         o_leaf[i] = put(f.leaf[i].data(), f.leaf[i].size() * 4);
         o_sib[i] = put(f.sibling[i].data(), f.sibling[i].size() * 4);
     }
+    lap("blob");
     d.release();
     CU(cudaMalloc(&d.base, blob.size()));
     d.bytes_alloc = blob.size();
+    lap("malloc");
     CU(cudaMemcpy(d.base, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    lap("memcpy");
     SceneView& v = d.view;
     memset(&v, 0, sizeof v);
     v.nodes = (const DevNode*)(d.base + o_nodes); v.sph = (const double*)(d.base + o_sph); v.sph_s = (const f4*)(d.base + o_sph_s);
@@ -381,7 +394,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     {   // worlds with exactly one BVH among at least one plain object, no medium, no predictor -> wf_extend_bvh1
         int n_bvh = 0, idx = -1;
         for (size_t i = 0; i < s->flat.objects.size(); ++i) if (s->flat.objects[i].kind == OBJ_BVH) { ++n_bvh; idx = (int)i; }
-        if (n_bvh == 1 && (s->flat.objects.size() > 1 || getenv("SHIM_FORCE_BVH1")) && !s->has_media && !k.use_hrpp && !getenv("SHIM_NO_BVH1")) k.bvh1_index = idx;
+        if (n_bvh == 1 && s->flat.objects.size() > 1 && !s->has_media && !k.use_hrpp && !getenv("SHIM_NO_BVH1")) k.bvh1_index = idx;
     }
     k.smem = s->dev->scene.smem;
     const int smem_extra = k.bvh1_index >= 0 ? SHIM_BVH1_SMEM_BYTES : 0;
@@ -489,8 +502,22 @@ SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_rende
     int rc = ensure_device(s);
     if (rc < 0) return rc;
     Wavefront& w = g_wf[s->dev->device & 63];
-    // persistent device framebuffer + pinned staging: no allocation on the per-call path
+    // a page-locked destination (shim_host_alloc, or memory the caller registered) takes the D2H directly
+    bool pinned_out = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess) pinned_out = at.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
     if (w.d_out.n < fb) CU(w.d_out.alloc(fb));
+    if (pinned_out) {
+        rc = shim_render_device(s, cam, p, w.d_out.p, stats, nullptr);
+        if (rc != SHIM_OK) return rc;
+        CU(cudaMemcpyAsync(out, w.d_out.p, fb * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+        CU(cudaStreamSynchronize(nullptr));
+        return SHIM_OK;
+    }
+    // otherwise: persistent pinned staging, no allocation on the per-call path
     if (w.h_out_n < fb) {
         if (w.h_out) cudaFreeHost(w.h_out);
         w.h_out = nullptr; w.h_out_n = 0;
@@ -529,6 +556,16 @@ SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_rende
         return set_err(SHIM_ERR_CUDA, std::string("framebuffer copy: ") + cudaGetErrorString(err0 != cudaSuccess ? err0 : err1));
     return SHIM_OK;
 }
+
+SHIM_API float* shim_host_alloc(size_t floats) {
+    float* p = nullptr;
+    if (cudaMallocHost(&p, (floats ? floats : 1) * sizeof(float)) != cudaSuccess) {
+        set_err(SHIM_ERR_CUDA, std::string("shim_host_alloc: ") + cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+SHIM_API void shim_host_free(float* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------------ gate 1
 SHIM_API int shim_trace_closest_device(shim_scene* s, const float* d_rays, int64_t n, float t_min, float t_max, uint64_t seed,

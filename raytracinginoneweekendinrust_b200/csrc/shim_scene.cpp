@@ -79,6 +79,15 @@ static int bvh_height(const std::vector<HostBvhNode>& nodes, int i) {  // BvhNod
     return (l > r ? l : r) + 1;
 }
 
+static int build_device_tree(const SceneBuilder& sb, const HostHittable& b, std::vector<HostBvhNode>& out);
+// The device tree belongs to the BVH's construction (Bvh::new, bvh.rs:46-62, is scene-build time in the reference
+// too), so shim_commit only lays it out.
+static void attach_device_tree(const SceneBuilder& sb, HostHittable& bvh) {
+    bvh.dev_root = build_device_tree(sb, bvh, bvh.dev_nodes);
+    if (bvh.dev_root >= 0) bvh.dev_height = bvh_height(bvh.dev_nodes, bvh.dev_root);
+    else bvh.dev_nodes.clear();
+}
+
 int SceneBuilder::build_bvh(int list, float t0, float t1, uint64_t axis_seed, bool predictor) {
     if (!ok_hit(list) || hittables[list].kind != H_LIST) { err = "shim_bvh: not a list"; return SHIM_ERR_INVALID_; }
     std::vector<int> objs = hittables[list].items;
@@ -123,6 +132,7 @@ int SceneBuilder::build_bvh(int list, float t0, float t1, uint64_t axis_seed, bo
     };
     bvh.root = rec(objs.data(), objs.size());
     bvh.height = bvh_height(bvh.nodes, bvh.root);
+    attach_device_tree(*this, bvh);
     return add_hittable(bvh);
 }
 
@@ -161,6 +171,7 @@ int SceneBuilder::bvh_from_nodes(int n, const int32_t* left, const int32_t* righ
         }
     }
     bvh.height = bvh_height(bvh.nodes, root);
+    attach_device_tree(*this, bvh);
     return add_hittable(bvh);
 }
 
@@ -320,7 +331,8 @@ namespace {
 struct Flattener {
     SceneBuilder& sb;
     FlatScene& fs;
-    std::unordered_map<int, uint32_t> prim_of;   // hittable id -> prim_ref
+    std::vector<uint32_t> prim_of;               // hittable id -> prim_ref (NO_PRIM: not flattened yet); dense: ids are small
+    static constexpr uint32_t NO_PRIM = 0xffffffffu;
     std::unordered_map<int, int> bvh_base;       // hittable id -> first node index
     std::unordered_map<int, int> bvh_pred;       // hittable id -> predictor index
     std::unordered_map<int, int> bvh_root, bvh_nodes;
@@ -331,8 +343,8 @@ struct Flattener {
     int fail(int code, const std::string& m) { sb.err = m; status = code; return code; }
 
     uint32_t add_prim(int hid) {
-        auto it = prim_of.find(hid);
-        if (it != prim_of.end()) return it->second;
+        if (prim_of.size() < sb.hittables.size()) prim_of.resize(sb.hittables.size(), NO_PRIM);
+        if (prim_of[hid] != NO_PRIM) return prim_of[hid];
         const HostHittable& h = sb.hittables[hid];
         const float* p = h.p;
         uint32_t ref = 0;
@@ -390,10 +402,9 @@ struct Flattener {
         // device tree: SAH rebuild by default, the recorded (bvh.rs) topology when asked for
         HostHittable sah_tree;
         if (!sb.device_reference_topology) {
+            if (rec.dev_root < 0) { fail(SHIM_ERR_UNSUPPORTED_, "a BVH may only contain primitives and cubes"); return -1; }
             sah_tree.t0 = rec.t0; sah_tree.t1 = rec.t1; sah_tree.predictor = rec.predictor;
-            sah_tree.root = build_device_tree(sb, rec, sah_tree.nodes);
-            if (sah_tree.root < 0) { fail(SHIM_ERR_UNSUPPORTED_, "a BVH may only contain primitives and cubes"); return -1; }
-            sah_tree.height = bvh_height(sah_tree.nodes, sah_tree.root);
+            sah_tree.nodes = rec.dev_nodes; sah_tree.root = rec.dev_root; sah_tree.height = rec.dev_height;
         }
         const HostHittable& b = sb.device_reference_topology ? rec : sah_tree;
         int base = (int)fs.nodes.size();
@@ -403,7 +414,7 @@ struct Flattener {
         if (b.height > SHIM_MAX_BVH_HEIGHT) { fail(SHIM_ERR_UNSUPPORTED_, "BVH taller than the traversal stack"); return -1; }
         // ties (bvh.rs:409-415) go to the primitive that is latest in the left-to-right leaf order of the RECORDED
         // bvh.rs tree, whichever tree the device walks
-        std::unordered_map<int, int> ref_rank, ref_sibling;   // sibling: the other primitive of a recorded two-primitive leaf
+        std::vector<int> ref_rank(sb.hittables.size(), 0), ref_sibling(sb.hittables.size(), -1);   // sibling: the other primitive of a recorded two-primitive leaf
         for (const HostBvhNode& n : rec.nodes)
             if (n.left < 0 && n.right < 0 && n.left != n.right) { ref_sibling[~n.left] = ~n.right; ref_sibling[~n.right] = ~n.left; }
         {
@@ -427,16 +438,15 @@ struct Flattener {
                 uint32_t ref = add_prim(h);
                 fs.rank[prim_type(ref)][prim_index(ref)] = ref_rank[h];
                 fs.leaf[prim_type(ref)][prim_index(ref)] = base + i;
-                auto sb_it = ref_sibling.find(h);
-                if (sb_it != ref_sibling.end()) pending_siblings.push_back({ref, sb_it->second});
+                if (ref_sibling[h] >= 0) pending_siblings.push_back({ref, ref_sibling[h]});
             };
             if (n.left >= 0) walk(n.left); else leaf_child(n.left);
             if (n.right >= 0) walk(n.right); else if (!dup) leaf_child(n.right);
         };
         walk(b.root);
         for (auto& ps : pending_siblings) {
-            auto it = prim_of.find(ps.second);
-            if (it != prim_of.end()) fs.sibling[prim_type(ps.first)][prim_index(ps.first)] = (int)it->second;
+            if ((size_t)ps.second < prim_of.size() && prim_of[ps.second] != NO_PRIM)
+                fs.sibling[prim_type(ps.first)][prim_index(ps.first)] = (int)prim_of[ps.second];
         }
         if (bad) { fail(SHIM_ERR_UNSUPPORTED_, "a BVH may only contain primitives and cubes"); return -1; }
         for (size_t i = 0; i < b.nodes.size(); ++i) {

@@ -35,6 +35,8 @@ struct HostHittable {
     std::vector<int> items;          // list
     std::vector<HostBvhNode> nodes;  // bvh (post-order, root last when built here)
     int root = -1, height = 0;
+    std::vector<HostBvhNode> dev_nodes;   // bvh: the binned-SAH tree the kernels walk, built with the BVH (Bvh::new's stand-in)
+    int dev_root = -1, dev_height = 0;    // dev_root < 0: not built (unsupported member: reported at commit)
     float t0 = 0, t1 = 0;
     bool predictor = false;
     float sin_t = 0, cos_t = 1;      // rotate_y

@@ -46,3 +46,10 @@ for kv in [a for a in os.environ.get('PROBE_ENVS', '').split(',') if a]:
         s.render(cfg.camera, P(capi.RENDER_PROFILE))
         del os.environ['SHIM_TRACE']
     del os.environ[k]
+if '--alive' in sys.argv:
+    prev = 0
+    out = []
+    for d in range(1, 51):
+        _, st = s.render(cfg.camera, api.make_params(cfg.width, cfg.height, spp, d, background=info.background, seed=0))
+        out.append(st.rays - prev); prev = st.rays
+    print("alive per bounce:", out)
