@@ -21,6 +21,7 @@
 #ifndef SHIMMER_B200_H
 #define SHIMMER_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
