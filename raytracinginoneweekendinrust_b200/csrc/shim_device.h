@@ -98,13 +98,35 @@ SHIM_HD f3 random_in_unit_disk(Rng& r) {
     }
 }
 // materials/utils.rs:6-19
-SHIM_HD f3 random_in_unit_sphere(Rng& r) {
+SHIM_HD f3 random_in_unit_sphere_stream(Rng& r) {
     for (;;) {
         float a = rng_range(r, -1.0f, 1.0f);
         float b = rng_range(r, -1.0f, 1.0f);
         float c = rng_range(r, -1.0f, 1.0f);
         f3 p = mk3(a, b, c);
         if (dot3(p, p) < 1.0f) return p;
+    }
+}
+// The same draws when the stream is at its start (always the case in scatter: the sphere sample is the first draw of
+// its stage).  Try k is words 3k..3k+2 of the stream, so three Philox blocks hold exactly four tries; written out,
+// the word-to-try assignment is static and the per-draw refill branch and word select of rng_u32 disappear
+// (they were a quarter of wf_shade's instructions).  Leaves the stream where the generic loop would.
+SHIM_HD float rng_word_pm1(uint32_t w) { return (float)(w >> 9) * (1.0f / 8388608.0f) * 2.0f + -1.0f; }  // rng_range(r, -1, 1)
+SHIM_HD f3 random_in_unit_sphere(Rng& r) {
+    if (r.j != 0) return random_in_unit_sphere_stream(r);
+    for (uint32_t blk = 0;; blk += 3) {
+        uint32_t a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3;
+        philox4x32_10(r.pixel, r.sample, r.dim, blk, r.k0, r.k1, a0, a1, a2, a3);
+        f3 p = mk3(rng_word_pm1(a0), rng_word_pm1(a1), rng_word_pm1(a2));
+        if (dot3(p, p) < 1.0f) { r.j = 4u * blk + 3u; r.b0 = a0; r.b1 = a1; r.b2 = a2; r.b3 = a3; return p; }
+        philox4x32_10(r.pixel, r.sample, r.dim, blk + 1u, r.k0, r.k1, b0, b1, b2, b3);
+        p = mk3(rng_word_pm1(a3), rng_word_pm1(b0), rng_word_pm1(b1));
+        if (dot3(p, p) < 1.0f) { r.j = 4u * blk + 6u; r.b0 = b0; r.b1 = b1; r.b2 = b2; r.b3 = b3; return p; }
+        philox4x32_10(r.pixel, r.sample, r.dim, blk + 2u, r.k0, r.k1, c0, c1, c2, c3);
+        p = mk3(rng_word_pm1(b2), rng_word_pm1(b3), rng_word_pm1(c0));
+        if (dot3(p, p) < 1.0f) { r.j = 4u * blk + 9u; r.b0 = c0; r.b1 = c1; r.b2 = c2; r.b3 = c3; return p; }
+        p = mk3(rng_word_pm1(c1), rng_word_pm1(c2), rng_word_pm1(c3));
+        if (dot3(p, p) < 1.0f) { r.j = 4u * blk + 12u; r.b0 = c0; r.b1 = c1; r.b2 = c2; r.b3 = c3; return p; }
     }
 }
 
