@@ -88,6 +88,7 @@ SHIM_HD float rng_range(Rng& r, float lo, float hi) {
     float s = hi - lo;
     return (float)(rng_u32(r) >> 9) * (1.0f / 8388608.0f) * s + lo;
 }
+SHIM_HD float rng_word_pm1(uint32_t w) { return (float)(w >> 9) * (1.0f / 8388608.0f) * 2.0f + -1.0f; }  // rng_range(r, -1, 1) on word w
 // utils.rs:9-17
 SHIM_HD f3 random_in_unit_disk(Rng& r) {
     for (;;) {
@@ -111,7 +112,6 @@ SHIM_HD f3 random_in_unit_sphere_stream(Rng& r) {
 // its stage).  Try k is words 3k..3k+2 of the stream, so three Philox blocks hold exactly four tries; written out,
 // the word-to-try assignment is static and the per-draw refill branch and word select of rng_u32 disappear
 // (they were a quarter of wf_shade's instructions).  Leaves the stream where the generic loop would.
-SHIM_HD float rng_word_pm1(uint32_t w) { return (float)(w >> 9) * (1.0f / 8388608.0f) * 2.0f + -1.0f; }  // rng_range(r, -1, 1)
 SHIM_HD f3 random_in_unit_sphere(Rng& r) {
     if (r.j != 0) return random_in_unit_sphere_stream(r);
     for (uint32_t blk = 0;; blk += 3) {
@@ -142,10 +142,38 @@ SHIM_HD Ray camera_get_ray(const CameraPod& c, float s, float t, Rng& rng) {
     return r;
 }
 // renderer.rs:141-143
+// renderer.rs:141-143 + camera.rs:96-106 from a stream at its start (the camera stage's first draws), written out
+// over Philox blocks like random_in_unit_sphere: words 0,1 jitter the pixel, disk try k is words 2+2k, 3+2k, the word
+// after the accepted try is the shutter time.
 SHIM_HD Ray camera_sample(const CameraPod& c, int x, int y, int width, int height, Rng& rng) {
-    float u = ((float)x + rng_uniform01(rng)) / (float)(width - 1);
-    float v = ((float)y + rng_uniform01(rng)) / (float)(height - 1);
-    return camera_get_ray(c, u, v, rng);
+    if (rng.j != 0) {
+        float u = ((float)x + rng_uniform01(rng)) / (float)(width - 1);
+        float v = ((float)y + rng_uniform01(rng)) / (float)(height - 1);
+        return camera_get_ray(c, u, v, rng);
+    }
+    uint32_t w0, w1, w2, w3;
+    philox4x32_10(rng.pixel, rng.sample, rng.dim, 0u, rng.k0, rng.k1, w0, w1, w2, w3);
+    const float s = ((float)x + (float)(w0 >> 8) * (1.0f / 16777216.0f)) / (float)(width - 1);
+    const float t = ((float)y + (float)(w1 >> 8) * (1.0f / 16777216.0f)) / (float)(height - 1);
+    f3 p = mk3(rng_word_pm1(w2), rng_word_pm1(w3), 0.0f);
+    bool accepted = dot3(p, p) < 1.0f;
+    uint32_t time_word;
+    for (uint32_t blk = 1;; ++blk) {
+        philox4x32_10(rng.pixel, rng.sample, rng.dim, blk, rng.k0, rng.k1, w0, w1, w2, w3);
+        if (accepted) { time_word = w0; rng.j = 4u * blk + 1u; break; }
+        p = mk3(rng_word_pm1(w0), rng_word_pm1(w1), 0.0f);
+        if (dot3(p, p) < 1.0f) { time_word = w2; rng.j = 4u * blk + 3u; break; }
+        p = mk3(rng_word_pm1(w2), rng_word_pm1(w3), 0.0f);
+        accepted = dot3(p, p) < 1.0f;
+    }
+    rng.b0 = w0; rng.b1 = w1; rng.b2 = w2; rng.b3 = w3;
+    f3 rd = c.lens_radius * p;
+    f3 offset = c.u * rd.x + c.v * rd.y;
+    Ray r;
+    r.o = c.origin + offset;
+    r.d = c.llc + s * c.horizontal + t * c.vertical - c.origin - offset;
+    r.time = (float)(time_word >> 9) * (1.0f / 8388608.0f) * (c.time1 - c.time0) + c.time0;   // rng_range(rng, time0, time1)
+    return r;
 }
 
 // ---------------------------------------------------------------------------- object-space ray

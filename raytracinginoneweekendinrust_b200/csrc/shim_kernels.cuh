@@ -130,8 +130,9 @@ __global__ void __launch_bounds__(256) wf_generate() {
     const uint32_t n = (uint32_t)(remaining < room ? remaining : room);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         unsigned long long g = first + j;
-        uint32_t s = (uint32_t)(g / p.npix);
-        uint32_t pi = (uint32_t)(g - (unsigned long long)s * p.npix);
+        uint32_t s, pi;
+        if (p.total_samples <= 0xffffffffull) { s = (uint32_t)g / p.npix; pi = (uint32_t)g - s * p.npix; }   // 32-bit divide when it fits
+        else { s = (uint32_t)(g / p.npix); pi = (uint32_t)(g - (unsigned long long)s * p.npix); }
         uint32_t pixel = p.pix_table[pi];
         int x = (int)(pixel % (uint32_t)p.width), y = (int)(pixel / (uint32_t)p.width);
         uint32_t sample = (uint32_t)p.sample_begin + s;
