@@ -58,6 +58,12 @@ for bb in range(0, 5):
         "octant": (d[:, 0] > 0) * 4 + (d[:, 1] > 0) * 2 + (d[:, 2] > 0),
         "origin.y<0.05 (ground)": (r[:, 1] < 0.05).astype(int),
         "ground x dir.y 4": (r[:, 1] < 0.05) * 4 + np.digitize(d[:, 1], [-0.3, 0.0, 0.3]),
+        "dir.y 16 levels": np.digitize(d[:, 1], np.linspace(-0.9, 0.9, 15)),
+        "dir.y 8 x xz-signs": np.digitize(d[:, 1], [-0.6, -0.3, -0.1, 0.0, 0.1, 0.3, 0.6]) * 4 + (d[:, 0] > 0) * 2 + (d[:, 2] > 0),
+        "dir.y 8 x origin quadrant": np.digitize(d[:, 1], [-0.6, -0.3, -0.1, 0.0, 0.1, 0.3, 0.6]) * 4 + (r[:, 0] > 4) * 2 + (r[:, 2] > 1),
+        "dir.y 8 x origin.y<0.05": np.digitize(d[:, 1], [-0.6, -0.3, -0.1, 0.0, 0.1, 0.3, 0.6]) * 2 + (r[:, 1] < 0.05),
+        "dir.y 8 x az 4": np.digitize(d[:, 1], [-0.6, -0.3, -0.1, 0.0, 0.1, 0.3, 0.6]) * 4 + np.digitize(np.arctan2(d[:, 2], d[:, 0]), [-np.pi/2, 0, np.pi/2]),
+        "dir.y 8 x az 8": np.digitize(d[:, 1], [-0.6, -0.3, -0.1, 0.0, 0.1, 0.3, 0.6]) * 8 + np.digitize(np.arctan2(d[:, 2], d[:, 0]), np.linspace(-np.pi, np.pi, 9)[1:-1]),
         "oracle (sorted by cost)": np.argsort(np.argsort(c)),
     }
     for name, k in keys.items():
