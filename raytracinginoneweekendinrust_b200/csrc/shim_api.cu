@@ -211,7 +211,7 @@ SHIM_API int shim_commit(shim_scene* s) {
         uint32_t off = 0;
         auto place = [&](uint32_t& o, uint32_t& b, size_t bytes) { o = off; b = (uint32_t)bytes; off += (uint32_t)((bytes + 127) & ~(size_t)127); };
         size_t tot = f.nodes.size() * sizeof(DevNode) + f.sph.size() * 8 + (f.msph.size() + f.rect.size() + f.tri.size() + f.cube.size()) * 16 +
-                     f.objects.size() * sizeof(DevObject);
+                     f.objects.size() * sizeof(DevObject) + f.sph_mat.size() * 4 + 16;
         if (tot <= 220 * 1024) {
             place(L.off_nodes, L.bytes_nodes, f.nodes.size() * sizeof(DevNode));
             place(L.off_sph, L.bytes_sph, f.sph.size() * 8);
@@ -220,6 +220,7 @@ SHIM_API int shim_commit(shim_scene* s) {
             place(L.off_tri, L.bytes_tri, f.tri.size() * 16);
             place(L.off_cube, L.bytes_cube, f.cube.size() * 16);
             place(L.off_objects, L.bytes_objects, f.objects.size() * sizeof(DevObject));
+            place(L.off_sph_mat, L.bytes_sph_mat, (f.sph_mat.size() * 4 + 15) & ~(size_t)15);   // bulk copies move 16-byte units (the blob pads every array)
             L.total = off;
         }
     }

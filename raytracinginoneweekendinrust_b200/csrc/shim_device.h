@@ -610,7 +610,12 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
     return h;
 }
 
-SHIM_HD int prim_material(const SceneView& sv, uint32_t ref) {
+// Every stored material reference is a word: material index | kind << 28 (the flattener packs the kind in, so the
+// closest-hit stage learns which material queue a hit goes to from the primitive record it already holds in
+// shared memory instead of a second, dependent load from the material table).
+SHIM_HD int mat_word_index(int w) { return w & 0x0fffffff; }
+SHIM_HD int mat_word_kind(int w) { return (int)((uint32_t)w >> 28); }
+SHIM_HD int prim_material_word(const SceneView& sv, uint32_t ref) {
     uint32_t i = prim_index(ref);
     switch (prim_type(ref)) {
     case PT_SPHERE: return sv.sph_mat[i];
@@ -620,10 +625,12 @@ SHIM_HD int prim_material(const SceneView& sv, uint32_t ref) {
     default: return f2i(sv.cube[2 * (size_t)i].w);
     }
 }
-SHIM_HD int hit_material(const SceneView& sv, const Hit& h) {
+SHIM_HD int prim_material(const SceneView& sv, uint32_t ref) { return mat_word_index(prim_material_word(sv, ref)); }
+SHIM_HD int hit_material_word(const SceneView& sv, const Hit& h) {
     const DevObject& ob = sv.objects[h.obj];
-    return (ob.flags & OBJ_MEDIUM) ? ob.phase_mat : prim_material(sv, h.prim);
+    return (ob.flags & OBJ_MEDIUM) ? ob.phase_mat : prim_material_word(sv, h.prim);
 }
+SHIM_HD int hit_material(const SceneView& sv, const Hit& h) { return mat_word_index(hit_material_word(sv, h)); }
 SHIM_HD int hit_handle(const SceneView& sv, const Hit& h) {
     if (h.obj < 0) return -1;
     const DevObject& ob = sv.objects[h.obj];
@@ -655,7 +662,7 @@ SHIM_HD void reconstruct_hit(const SceneView& sv, const Ray& ray, const Hit& h, 
     if (ob.flags & OBJ_MEDIUM) {  // hittable.rs:216-231
         rec.point = ray_at(ray, h.t);
         rec.normal = mk3(1.0f, 0.0f, 0.0f);
-        rec.t = h.t; rec.u = 0.0f; rec.v = 0.0f; rec.front_face = true; rec.material = ob.phase_mat;
+        rec.t = h.t; rec.u = 0.0f; rec.v = 0.0f; rec.front_face = true; rec.material = mat_word_index(ob.phase_mat);
         return;
     }
     Ray r = object_ray(ob, ray);
@@ -667,7 +674,7 @@ SHIM_HD void reconstruct_hit(const SceneView& sv, const Ray& ray, const Hit& h, 
         f3 n = (point - xyz(s)) / s.w;
         float u = 0.0f, v = 0.0f;
         if (need_uv) sphere_uv(n, u, v);
-        rec_new(rec, r, n, h.t, u, v, sv.sph_mat[i]);
+        rec_new(rec, r, n, h.t, u, v, mat_word_index(sv.sph_mat[i]));
         break;
     }
     case PT_MSPHERE: {

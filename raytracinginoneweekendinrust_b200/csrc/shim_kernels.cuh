@@ -35,8 +35,8 @@ enum { CNT_WORDS = CNT_U64_BASE + 2 * C64_COUNT };
 
 // shared-memory image of the scene arrays wf_extend walks (byte offsets, all multiples of 16)
 struct SmemLayout {
-    uint32_t off_nodes, off_sph, off_msph, off_rect, off_tri, off_cube, off_objects;
-    uint32_t bytes_nodes, bytes_sph, bytes_msph, bytes_rect, bytes_tri, bytes_cube, bytes_objects;
+    uint32_t off_nodes, off_sph, off_msph, off_rect, off_tri, off_cube, off_objects, off_sph_mat;
+    uint32_t bytes_nodes, bytes_sph, bytes_msph, bytes_rect, bytes_tri, bytes_cube, bytes_objects, bytes_sph_mat;
     uint32_t total;  // 0 = scene does not fit: walk it in global memory (L2)
 };
 
@@ -209,8 +209,9 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
                     atomicAdd(a + 2, t.z * p.bg[2]);
                 }
             } else {
-                int mat = hit_material(sv, h);
-                kind = mat_kind(sv, mat);
+                const int mw = hit_material_word(sv, h);
+                const int mat = mat_word_index(mw);
+                kind = mat_word_kind(mw);
                 hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat);
             }
         }
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
         __syncthreads();
         if (threadIdx.x == 0) {
             const SmemLayout& L = p.smem;
-            mbar_expect_tx(&bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects);
+            mbar_expect_tx(&bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects + L.bytes_sph_mat);
             if (L.bytes_nodes) bulk_g2s(smem + L.off_nodes, p.sv.nodes, L.bytes_nodes, &bar);
             if (L.bytes_sph) bulk_g2s(smem + L.off_sph, p.sv.sph, L.bytes_sph, &bar);
             if (L.bytes_msph) bulk_g2s(smem + L.off_msph, p.sv.msph, L.bytes_msph, &bar);
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
             if (L.bytes_tri) bulk_g2s(smem + L.off_tri, p.sv.tri, L.bytes_tri, &bar);
             if (L.bytes_cube) bulk_g2s(smem + L.off_cube, p.sv.cube, L.bytes_cube, &bar);
             if (L.bytes_objects) bulk_g2s(smem + L.off_objects, p.sv.objects, L.bytes_objects, &bar);
+            if (L.bytes_sph_mat) bulk_g2s(smem + L.off_sph_mat, p.sv.sph_mat, L.bytes_sph_mat, &bar);
         }
         sv.nodes = reinterpret_cast<const DevNode*>(smem + p.smem.off_nodes);
         sv.sph = reinterpret_cast<const double*>(smem + p.smem.off_sph);
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
         sv.tri = reinterpret_cast<const f4*>(smem + p.smem.off_tri);
         sv.cube = reinterpret_cast<const f4*>(smem + p.smem.off_cube);
         sv.objects = reinterpret_cast<const DevObject*>(smem + p.smem.off_objects);
+        sv.sph_mat = reinterpret_cast<const int*>(smem + p.smem.off_sph_mat);
         mbar_wait(&bar, 0);
     }
     extend_rays<COUNT, MEDIA, HRPP>(p, sv, cur, n);
@@ -307,8 +310,9 @@ __device__ __forceinline__ void bvh1_finish(const WfParams& p, const SceneView& 
                 atomicAdd(a + 2, t.z * p.bg[2]);
             }
         } else {
-            int mat = hit_material(sv, h);
-            kind = mat_kind(sv, mat);
+            const int mw = hit_material_word(sv, h);
+            const int mat = mat_word_index(mw);
+            kind = mat_word_kind(mw);
             hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat);
         }
     }
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend_bvh1() {
         __syncthreads();
         if (threadIdx.x == 0) {
             const SmemLayout& L = p.smem;
-            mbar_expect_tx(&bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects);
+            mbar_expect_tx(&bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects + L.bytes_sph_mat);
             if (L.bytes_nodes) bulk_g2s(smem + L.off_nodes, p.sv.nodes, L.bytes_nodes, &bar);
             if (L.bytes_sph) bulk_g2s(smem + L.off_sph, p.sv.sph, L.bytes_sph, &bar);
             if (L.bytes_msph) bulk_g2s(smem + L.off_msph, p.sv.msph, L.bytes_msph, &bar);
@@ -466,6 +470,7 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend_bvh1() {
             if (L.bytes_tri) bulk_g2s(smem + L.off_tri, p.sv.tri, L.bytes_tri, &bar);
             if (L.bytes_cube) bulk_g2s(smem + L.off_cube, p.sv.cube, L.bytes_cube, &bar);
             if (L.bytes_objects) bulk_g2s(smem + L.off_objects, p.sv.objects, L.bytes_objects, &bar);
+            if (L.bytes_sph_mat) bulk_g2s(smem + L.off_sph_mat, p.sv.sph_mat, L.bytes_sph_mat, &bar);
         }
         sv.nodes = reinterpret_cast<const DevNode*>(smem + p.smem.off_nodes);
         sv.sph = reinterpret_cast<const double*>(smem + p.smem.off_sph);
@@ -474,6 +479,7 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend_bvh1() {
         sv.tri = reinterpret_cast<const f4*>(smem + p.smem.off_tri);
         sv.cube = reinterpret_cast<const f4*>(smem + p.smem.off_cube);
         sv.objects = reinterpret_cast<const DevObject*>(smem + p.smem.off_objects);
+        sv.sph_mat = reinterpret_cast<const int*>(smem + p.smem.off_sph_mat);
         mbar_wait(&bar, 0);
     }
     extend_rays_bvh1<COUNT>(p, sv, cur, n, reinterpret_cast<Bvh1Entry*>(smem + (SMEM ? p.smem.total : 0u)));
@@ -598,10 +604,11 @@ __global__ void __launch_bounds__(128) wf_tail() {
                 atomicAdd(a + 2, thr.z * p.bg[2]);
                 break;
             }
-            int mat = hit_material(p.sv, h);
+            const int mw = hit_material_word(p.sv, h);
+            const int mat = mat_word_index(mw);
             ShadeOut so;
             so.cont = false;
-            switch (mat_kind(p.sv, mat)) {
+            switch (mat_word_kind(mw)) {
             case MAT_LAMBERTIAN: shade_one<MAT_LAMBERTIAN>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
             case MAT_METAL: shade_one<MAT_METAL>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
             case MAT_DIELECTRIC: shade_one<MAT_DIELECTRIC>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;

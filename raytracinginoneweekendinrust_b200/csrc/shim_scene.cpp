@@ -341,6 +341,11 @@ struct Flattener {
     struct Xf { bool translate = false, rotate = false; float d[3] = {0, 0, 0}; float s = 0, c = 1; int medium = -1; };
 
     int fail(int code, const std::string& m) { sb.err = m; status = code; return code; }
+    // material reference as the device stores it: index | kind << 28 (shim_device.h: mat_word_index / mat_word_kind)
+    int material_word(int mi) const {
+        if (mi < 0 || (size_t)mi >= sb.materials.size()) return mi;
+        return (int)((uint32_t)mi | ((uint32_t)sb.materials[mi].kind << 28));
+    }
 
     uint32_t add_prim(int hid) {
         if (prim_of.size() < sb.hittables.size()) prim_of.resize(sb.hittables.size(), NO_PRIM);
@@ -349,13 +354,14 @@ struct Flattener {
         const float* p = h.p;
         uint32_t ref = 0;
         auto bits = [](int i) { float f; memcpy(&f, &i, 4); return f; };
+        const int mat_word = material_word(h.material);
         switch (h.kind) {
         case H_SPHERE: {
             ref = prim_ref(PT_SPHERE, (uint32_t)fs.sph_s.size());
             double r = (double)p[3];
             fs.sph.push_back((double)p[0]); fs.sph.push_back((double)p[1]); fs.sph.push_back((double)p[2]); fs.sph.push_back(r * r);
             fs.sph_s.push_back(f4{p[0], p[1], p[2], p[3]});
-            fs.sph_mat.push_back(h.material);
+            fs.sph_mat.push_back(mat_word);
             fs.handle[PT_SPHERE].push_back(hid);
             break;
         }
@@ -363,25 +369,25 @@ struct Flattener {
             ref = prim_ref(PT_MSPHERE, (uint32_t)fs.handle[PT_MSPHERE].size());
             fs.msph.push_back(f4{p[0], p[1], p[2], p[8]});
             fs.msph.push_back(f4{p[3], p[4], p[5], p[6]});
-            fs.msph.push_back(f4{p[7], bits(h.material), 0, 0});
+            fs.msph.push_back(f4{p[7], bits(mat_word), 0, 0});
             fs.handle[PT_MSPHERE].push_back(hid);
             break;
         case H_RECT:
             ref = prim_ref(PT_RECT, (uint32_t)fs.handle[PT_RECT].size());
             fs.rect.push_back(f4{p[0], p[1], p[2], p[3]});
-            fs.rect.push_back(f4{p[4], bits(h.axis), bits(h.material), 0});
+            fs.rect.push_back(f4{p[4], bits(h.axis), bits(mat_word), 0});
             fs.handle[PT_RECT].push_back(hid);
             break;
         case H_TRI:
             ref = prim_ref(PT_TRI, (uint32_t)fs.handle[PT_TRI].size());
-            fs.tri.push_back(f4{p[0], p[1], p[2], bits(h.material)});
+            fs.tri.push_back(f4{p[0], p[1], p[2], bits(mat_word)});
             fs.tri.push_back(f4{p[3] - p[0], p[4] - p[1], p[5] - p[2], 0});  // edge1 = vertex1 - vertex0, triangle.rs:44
             fs.tri.push_back(f4{p[6] - p[0], p[7] - p[1], p[8] - p[2], 0});  // edge2
             fs.handle[PT_TRI].push_back(hid);
             break;
         default:  // H_CUBE
             ref = prim_ref(PT_CUBE, (uint32_t)fs.handle[PT_CUBE].size());
-            fs.cube.push_back(f4{p[0], p[1], p[2], bits(h.material)});
+            fs.cube.push_back(f4{p[0], p[1], p[2], bits(mat_word)});
             fs.cube.push_back(f4{p[3], p[4], p[5], 0});
             fs.handle[PT_CUBE].push_back(hid);
             break;
@@ -499,7 +505,7 @@ struct Flattener {
         ob.sin_t = xf.s; ob.cos_t = xf.c;
         if (xf.medium >= 0) {
             const HostHittable& m = sb.hittables[xf.medium];
-            ob.flags |= OBJ_MEDIUM; ob.handle = xf.medium; ob.neg_inv_density = m.neg_inv_density; ob.phase_mat = m.phase_mat;
+            ob.flags |= OBJ_MEDIUM; ob.handle = xf.medium; ob.neg_inv_density = m.neg_inv_density; ob.phase_mat = material_word(m.phase_mat);
         }
         fs.objects.push_back(ob);
     }
