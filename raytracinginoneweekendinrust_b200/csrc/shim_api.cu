@@ -265,6 +265,10 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
         w.grid_generate = sms * (per_sm > 0 ? per_sm : 1);
         w.grid_tail = sms * 2;
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
     }
     size_t fb = (size_t)p.width * p.height * 3;
     if (w.accum.n != fb) CU(w.accum.alloc(fb));
@@ -285,6 +289,15 @@ static void launch_extend(const WfParams& k, int grid, uint32_t smem, cudaStream
         const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES;
         if (S) { if (C) wf_extend_bvh1<true, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<true, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
         else   { if (C) wf_extend_bvh1<false, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<false, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
+        return;
+    }
+    if (k.solo) {   // one plain Bvh, scene image in shared memory
+        switch (k.solo) {
+        case 640: wf_extend_solo<false, 640><<<grid, 640, smem, st>>>(); break;
+        case 768: wf_extend_solo<false, 768><<<grid, 768, smem, st>>>(); break;
+        case 896: wf_extend_solo<false, 896><<<grid, 896, smem, st>>>(); break;
+        default: wf_extend_solo<false, 1024><<<grid, 1024, smem, st>>>(); break;
+        }
         return;
     }
 #define SHIM_LAUNCH(SS, CC, MM, HH) wf_extend<SS, CC, MM, HH><<<grid, SHIM_EXTEND_THREADS, smem, st>>>()
@@ -317,7 +330,7 @@ enum { SHIM_CHUNK = 4 };  // iterations per done-flag readback of the host-drive
 static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
     uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
                    ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
-                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40);
+                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));
@@ -401,6 +414,12 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     const int smem_extra = k.bvh1_index >= 0 ? SHIM_BVH1_SMEM_BYTES : 0;
     const bool use_smem = k.smem.total != 0 && (int)k.smem.total + smem_extra <= w.max_smem - 1024 && !getenv("SHIM_NO_SMEM");
     if (!use_smem) k.smem.total = 0;
+    k.solo = 0;
+    if (use_smem && !k.count_nodes && !k.use_hrpp && !s->has_media && s->flat.objects.size() == 1 && s->flat.objects[0].kind == OBJ_BVH &&
+        (s->flat.objects[0].flags & ~OBJ_PREDICTOR) == 0) {
+        k.solo = 768;
+        if (const char* e = getenv("SHIM_SOLO")) k.solo = atoi(e);
+    }
     k.tail_threshold = 32768;
     if (const char* e = getenv("SHIM_TAIL")) k.tail_threshold = (uint32_t)atoi(e);
 

@@ -610,6 +610,18 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
     return h;
 }
 
+// closest_hit for a world that is exactly one plain Bvh (no Translate / RotateY / medium / predictor), e.g. the
+// Book-1 scene (main.rs:185-251): no object loop, no object-space ray, fewer live registers in wf_extend_solo.
+template <bool COUNT>
+SHIM_HD Hit closest_hit_solo(const SceneView& sv, const Ray& ray, float t_min, float t_max, TraceCounters* cnt) {
+    Hit h; h.t = t_max; h.obj = -1; h.prim = 0; h.face = 0;
+    RayCtx c;
+    make_ctx(c, ray);
+    BvhBest best;
+    if (bvh_closest<COUNT>(sv, sv.objects[0].ref, c, t_min, t_max, best, cnt)) { h.t = best.t; h.obj = 0; h.prim = best.prim; h.face = best.face; }
+    return h;
+}
+
 // Every stored material reference is a word: material index | kind << 28 (the flattener packs the kind in, so the
 // closest-hit stage learns which material queue a hit goes to from the primitive record it already holds in
 // shared memory instead of a second, dependent load from the material table).

@@ -61,6 +61,7 @@ struct WfParams {
     float bg[3];
     uint64_t seed;
     int has_media, count_nodes, use_hrpp;
+    int solo;         // > 0: the world is exactly one plain Bvh: wf_extend_solo with this many threads per block
     int bvh1_index;   // >= 0: the world is one BVH object (this one) among plain primitives, no medium: wf_extend_bvh1 applies
     SmemLayout smem;
     unsigned long long loop_handle;   // conditional handle of the CUDA-graph WHILE node the iteration runs in (0: host-driven loop)
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(256) wf_generate() {
 }
 
 // ---------------------------------------------------------------------------- extend
-template <bool COUNT, bool MEDIA, bool HRPP>
+template <bool COUNT, bool MEDIA, bool HRPP, bool SOLO = false>
 __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& sv, int cur, uint32_t n) {
     const uint32_t n_round = (n + 31u) & ~31u;
     const uint32_t lane = threadIdx.x & 31u;
@@ -197,7 +198,7 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
             }
             TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
             Hit h; h.obj = -1; h.t = 0; h.prim = 0; h.face = 0;
-            if (!poisoned) h = closest_hit<COUNT, HRPP>(sv, r, 0.001f, SHIM_INF, rng, &tc);
+            if (!poisoned) h = SOLO ? closest_hit_solo<COUNT>(sv, r, 0.001f, SHIM_INF, &tc) : closest_hit<COUNT, HRPP>(sv, r, 0.001f, SHIM_INF, rng, &tc);
             nodes += tc.nodes; prims += tc.prims; h_tp += tc.hrpp_tp; h_fp += tc.hrpp_fp; h_none += tc.hrpp_none;
             if (poisoned) {
                 // path ends without a contribution
@@ -244,6 +245,35 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
     }
 }
 
+// TMA-stages the arrays the walk reads into the block's shared memory (scene images up to ~220 KB)
+__device__ __forceinline__ SceneView stage_scene(const WfParams& p, unsigned char* smem, uint64_t* bar) {
+    SceneView sv = p.sv;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const SmemLayout& L = p.smem;
+        mbar_expect_tx(bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects + L.bytes_sph_mat);
+        if (L.bytes_nodes) bulk_g2s(smem + L.off_nodes, p.sv.nodes, L.bytes_nodes, bar);
+        if (L.bytes_sph) bulk_g2s(smem + L.off_sph, p.sv.sph, L.bytes_sph, bar);
+        if (L.bytes_msph) bulk_g2s(smem + L.off_msph, p.sv.msph, L.bytes_msph, bar);
+        if (L.bytes_rect) bulk_g2s(smem + L.off_rect, p.sv.rect, L.bytes_rect, bar);
+        if (L.bytes_tri) bulk_g2s(smem + L.off_tri, p.sv.tri, L.bytes_tri, bar);
+        if (L.bytes_cube) bulk_g2s(smem + L.off_cube, p.sv.cube, L.bytes_cube, bar);
+        if (L.bytes_objects) bulk_g2s(smem + L.off_objects, p.sv.objects, L.bytes_objects, bar);
+        if (L.bytes_sph_mat) bulk_g2s(smem + L.off_sph_mat, p.sv.sph_mat, L.bytes_sph_mat, bar);
+    }
+    sv.nodes = reinterpret_cast<const DevNode*>(smem + p.smem.off_nodes);
+    sv.sph = reinterpret_cast<const double*>(smem + p.smem.off_sph);
+    sv.msph = reinterpret_cast<const f4*>(smem + p.smem.off_msph);
+    sv.rect = reinterpret_cast<const f4*>(smem + p.smem.off_rect);
+    sv.tri = reinterpret_cast<const f4*>(smem + p.smem.off_tri);
+    sv.cube = reinterpret_cast<const f4*>(smem + p.smem.off_cube);
+    sv.objects = reinterpret_cast<const DevObject*>(smem + p.smem.off_objects);
+    sv.sph_mat = reinterpret_cast<const int*>(smem + p.smem.off_sph_mat);
+    mbar_wait(bar, 0);
+    return sv;
+}
+
 #ifndef SHIM_EXTEND_THREADS
 #define SHIM_EXTEND_THREADS 640
 #endif
@@ -282,6 +312,20 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
         mbar_wait(&bar, 0);
     }
     extend_rays<COUNT, MEDIA, HRPP>(p, sv, cur, n);
+}
+
+// The same kernel for worlds that are one plain Bvh and nothing else (Book-1): closest_hit_solo needs fewer registers,
+// so more warps are resident to cover the walk's dependent latencies.
+template <bool COUNT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) wf_extend_solo() {
+    const WfParams& p = g_p;
+    const int cur = (int)p.cnt[CNT_CUR];
+    const uint32_t n = p.cnt[cur];
+    if (blockIdx.x * blockDim.x >= n) return;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    SceneView sv = stage_scene(p, smem, &bar);
+    extend_rays<COUNT, false, false, true>(p, sv, cur, n);
 }
 
 // ---------------------------------------------------------------------------- extend, one-BVH worlds
