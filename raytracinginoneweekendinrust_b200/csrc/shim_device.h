@@ -310,8 +310,11 @@ SHIM_HD bool hit_cube(const f4* q, const Ray& r, float t_min, float t_max, float
     return any;
 }
 
+// ONLY >= 0: the caller knows every primitive it can meet is of that type (a Bvh of spheres only): no dispatch
+template <int ONLY = -1>
 SHIM_HD bool hit_prim(const SceneView& sv, uint32_t ref, const RayCtx& c, float t_min, float t_max, float& t, int& face) {
     uint32_t i = prim_index(ref);
+    if (ONLY == PT_SPHERE) return hit_sphere(sv.sph + 4 * (size_t)i, c.r, t_min, t_max, t);
     switch (prim_type(ref)) {
     case PT_SPHERE: return hit_sphere(sv.sph + 4 * (size_t)i, c.r, t_min, t_max, t);
     case PT_MSPHERE: return hit_msphere(sv.msph + 3 * (size_t)i, c.r, t_min, t_max, t);
@@ -357,16 +360,17 @@ struct BvhBest { float t; uint32_t prim; int face; bool any; };
 // f32 t's and the later leaf wins.  Inside one recorded two-primitive leaf it tests the right child against the LEFT
 // child's f32 t, which an f64 sphere root can exceed by the rounding: the right one wins only if it is still a hit
 // under that bound.  Returns whether the candidate replaces the current best.
+template <int ONLY = -1>
 SHIM_HD bool tie_goes_to_candidate(const SceneView& sv, const RayCtx& c, float t_min, uint32_t cand, uint32_t best, float t) {
     const bool later = table_of(sv.rank, prim_type(cand))[prim_index(cand)] > table_of(sv.rank, prim_type(best))[prim_index(best)];
     if (table_of(sv.sibling, prim_type(cand))[prim_index(cand)] != (int)best) return later;
     float t2; int f2 = 0;
-    const bool right_survives = hit_prim(sv, later ? cand : best, c, t_min, t, t2, f2);
+    const bool right_survives = hit_prim<ONLY>(sv, later ? cand : best, c, t_min, t, t2, f2);
     return later ? right_survives : !right_survives;
 }
 
 #define SHIM_STACK_END 0x7fffffff
-template <bool COUNT>
+template <bool COUNT, int ONLY = -1>
 SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, float t_min, float t_max, BvhBest& best,
                          TraceCounters* cnt) {
     best.t = t_max; best.prim = 0; best.face = 0; best.any = false;
@@ -408,9 +412,9 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
             // the primitive sees the widened bound too (an identical sphere's f64 root can lie just above the
             // f32-rounded best.t); what counts is its f32 t: closer wins, an exact tie goes to the later leaf
             // of the recorded tree (bvh.rs:409-415), anything beyond best.t is not a hit
-            if (hit_prim(sv, ref, c, t_min, t_cull, t, face) && !(t > best.t)) {
+            if (hit_prim<ONLY>(sv, ref, c, t_min, t_cull, t, face) && !(t > best.t)) {
                 bool take = !best.any || t < best.t;
-                if (!take) take = tie_goes_to_candidate(sv, c, t_min, ref, best.prim, t);
+                if (!take) take = tie_goes_to_candidate<ONLY>(sv, c, t_min, ref, best.prim, t);
                 if (take) { best.t = t; best.prim = ref; best.face = face; best.any = true; t_cull = t + fabsf(t) * 3.8146973e-06f; }
             }
             cur = sp > 0 ? stack[--sp] : SHIM_STACK_END;
@@ -612,13 +616,13 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
 
 // closest_hit for a world that is exactly one plain Bvh (no Translate / RotateY / medium / predictor), e.g. the
 // Book-1 scene (main.rs:185-251): no object loop, no object-space ray, fewer live registers in wf_extend_solo.
-template <bool COUNT>
+template <bool COUNT, int ONLY = -1>
 SHIM_HD Hit closest_hit_solo(const SceneView& sv, const Ray& ray, float t_min, float t_max, TraceCounters* cnt) {
     Hit h; h.t = t_max; h.obj = -1; h.prim = 0; h.face = 0;
     RayCtx c;
     make_ctx(c, ray);
     BvhBest best;
-    if (bvh_closest<COUNT>(sv, sv.objects[0].ref, c, t_min, t_max, best, cnt)) { h.t = best.t; h.obj = 0; h.prim = best.prim; h.face = best.face; }
+    if (bvh_closest<COUNT, ONLY>(sv, sv.objects[0].ref, c, t_min, t_max, best, cnt)) { h.t = best.t; h.obj = 0; h.prim = best.prim; h.face = best.face; }
     return h;
 }
 

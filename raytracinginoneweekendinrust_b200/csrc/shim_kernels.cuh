@@ -61,6 +61,7 @@ struct WfParams {
     float bg[3];
     uint64_t seed;
     int has_media, count_nodes, use_hrpp;
+    int solo_only;    // wf_extend_solo: the one primitive type of the Bvh (PT_*), or -1 when mixed
     int solo;         // > 0: the world is exactly one plain Bvh: wf_extend_solo with this many threads per block
     int bvh1_index;   // >= 0: the world is one BVH object (this one) among plain primitives, no medium: wf_extend_bvh1 applies
     SmemLayout smem;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256) wf_generate() {
 }
 
 // ---------------------------------------------------------------------------- extend
-template <bool COUNT, bool MEDIA, bool HRPP, bool SOLO = false>
+template <bool COUNT, bool MEDIA, bool HRPP, bool SOLO = false, int ONLY = -1>
 __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& sv, int cur, uint32_t n) {
     const uint32_t n_round = (n + 31u) & ~31u;
     const uint32_t lane = threadIdx.x & 31u;
@@ -198,7 +199,7 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
             }
             TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
             Hit h; h.obj = -1; h.t = 0; h.prim = 0; h.face = 0;
-            if (!poisoned) h = SOLO ? closest_hit_solo<COUNT>(sv, r, 0.001f, SHIM_INF, &tc) : closest_hit<COUNT, HRPP>(sv, r, 0.001f, SHIM_INF, rng, &tc);
+            if (!poisoned) h = SOLO ? closest_hit_solo<COUNT, ONLY>(sv, r, 0.001f, SHIM_INF, &tc) : closest_hit<COUNT, HRPP>(sv, r, 0.001f, SHIM_INF, rng, &tc);
             nodes += tc.nodes; prims += tc.prims; h_tp += tc.hrpp_tp; h_fp += tc.hrpp_fp; h_none += tc.hrpp_none;
             if (poisoned) {
                 // path ends without a contribution
@@ -210,7 +211,7 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
                     atomicAdd(a + 2, t.z * p.bg[2]);
                 }
             } else {
-                const int mw = hit_material_word(sv, h);
+                const int mw = (SOLO && ONLY == PT_SPHERE) ? sv.sph_mat[prim_index(h.prim)] : hit_material_word(sv, h);
                 const int mat = mat_word_index(mw);
                 kind = mat_word_kind(mw);
                 hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat);
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
 
 // The same kernel for worlds that are one plain Bvh and nothing else (Book-1): closest_hit_solo needs fewer registers,
 // so more warps are resident to cover the walk's dependent latencies.
-template <bool COUNT, int THREADS>
+template <bool COUNT, int THREADS, int ONLY>
 __global__ void __launch_bounds__(THREADS, 1) wf_extend_solo() {
     const WfParams& p = g_p;
     const int cur = (int)p.cnt[CNT_CUR];
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_solo() {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     SceneView sv = stage_scene(p, smem, &bar);
-    extend_rays<COUNT, false, false, true>(p, sv, cur, n);
+    extend_rays<COUNT, false, false, true, ONLY>(p, sv, cur, n);
 }
 
 // ---------------------------------------------------------------------------- extend, one-BVH worlds
