@@ -617,7 +617,7 @@ __device__ __forceinline__ void loop_publish(const WfParams& p, bool done) {
     p.cnt[CNT_DONE] = done ? 1u : 0u;
     if (p.loop_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)p.loop_handle, done ? 0u : 1u);
 }
-template <bool HRPP>
+template <bool HRPP, bool SOLO = false, int ONLY = -1>
 __global__ void __launch_bounds__(128) wf_tail() {
     const WfParams& p = g_p;
     const int cur = (int)p.cnt[CNT_CUR];
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(128) wf_tail() {
             rng_key(rng, (uint32_t)bounce, STAGE_INTERSECT);
             ++traced;
             if (ray_has_nan(r)) break;  // see extend_rays
-            Hit h = closest_hit<false, HRPP>(p.sv, r, 0.001f, SHIM_INF, rng, &tc);
+            Hit h = SOLO ? closest_hit_solo<false, ONLY>(p.sv, r, 0.001f, SHIM_INF, &tc) : closest_hit<false, HRPP>(p.sv, r, 0.001f, SHIM_INF, rng, &tc);
             if (h.obj < 0) {
                 float* a = p.accum + 3 * (size_t)pixel;
                 atomicAdd(a + 0, thr.x * p.bg[0]);
