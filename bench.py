@@ -312,7 +312,7 @@ def main_gpu(args):
                 traffic_note = {"captured_launch_rays": tj.get("rays_per_captured_launch"),
                                 "captured_launch_algorithmic_bytes": hbm_bytes_per_ray * tj.get("rays_per_captured_launch", 0),
                                 "source": tj.get("source")}
-        roofline = {"bound": "hbm", "kernel": "wf_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": capi.Stats.EXTEND_KERNELS.get(int(prof_stats[0].extend_variant), "wf_extend") if prof_stats else "wf_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_detail": traffic_note, "peak_source": peak_src,
                     "algorithmic_bytes_per_ray": hbm_bytes_per_ray,
                     "algorithmic_bytes_per_launch": hbm_bytes_per_ray * rays_rank0 / max(1, ext_launch),

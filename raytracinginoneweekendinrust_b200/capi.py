@@ -75,7 +75,10 @@ class Stats(C.Structure):
         ("hrpp_true_positive", C.c_uint64), ("hrpp_false_positive", C.c_uint64), ("hrpp_no_prediction", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("iterations", C.c_uint64), ("device_ms", C.c_double),
         ("extend_ms", C.c_double), ("shade_ms", C.c_double), ("generate_ms", C.c_double), ("extend_launches", C.c_uint64),
+        ("extend_variant", C.c_uint64),
     ]
+
+    EXTEND_KERNELS = {0: "wf_extend", 1: "wf_extend_bvh1", 2: "wf_extend_solo"}
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -504,6 +504,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         stats->hrpp_false_positive = c64[C64_HRPP_FP];
         stats->hrpp_no_prediction = c64[C64_HRPP_NONE];
         stats->iterations = w.h_flags[32 + CNT_ITER];
+        stats->extend_variant = k.solo ? 2u : (k.bvh1_index >= 0 ? 1u : 0u);
         // four kernels per executed iteration body (the last body may find the queue already empty) + wf_finalize
         stats->kernel_launches = 4ull * w.h_flags[32 + CNT_BODIES] + 1ull;
         float ms = 0;

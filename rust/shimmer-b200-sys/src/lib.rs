@@ -77,6 +77,7 @@ pub struct shim_stats {
     pub shade_ms: f64,
     pub generate_ms: f64,
     pub extend_launches: u64,
+    pub extend_variant: u64,
 }
 
 extern "C" {
