@@ -154,6 +154,7 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    result_out = _claim_stdout()
     cfg, W, H, spp = workload(args)
     r = run_cpu(args, args.steps, args.warmup, budget_s=120.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["mrays"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -164,11 +165,21 @@ def main_reference(args):
             "cpu_baseline": {"value": r["mrays"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference is Rust (no rustc here): C++ restatement in oracle/ run in reference mode on the host cores"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=result_out, flush=True)
 
 
 # -------------------------------------------------------------------------------------------- GPU arm
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries under us write there too (NCCL prints its version banner to
+    stdout): keep a private handle on the real stdout for the result line and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main_gpu(args):
+    result_out = _claim_stdout()
     import torch
     import torch.distributed as dist
     from raytracinginoneweekendinrust_b200 import api, capi, distributed, scenes
@@ -347,7 +358,7 @@ def main_gpu(args):
                 "gpu_launches": int(sum(s.kernel_launches for s in stats)),
                 "iterations_per_step": float(np.mean([s.iterations for s in stats])),
                 "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
