@@ -112,3 +112,46 @@ def test_depth_limit_and_empty_cases():
     np.testing.assert_allclose(img1, ref1, atol=1e-6)
     p, t = g.trace_closest(np.zeros((0, 7), np.float32))
     assert len(p) == 0 and len(t) == 0
+
+
+def _render_with_env(g, cam, params, env, out=None):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return g.render(cam, params, out=out)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_kernel_variants_agree():
+    """The device-side WHILE-node loop vs the host-driven loop, wf_extend_solo vs the generic wf_extend and wf_tail
+    vs plain iterations trace the same rays and give the same image (radiance sums differ only in atomicAdd order)."""
+    g, o, info = build_pair("random-spheres")
+    cam = CAMERAS["random-spheres"]
+    p = api.make_params(192, 128, 6, 50, background=info.background, seed=5)
+    ref, st = g.render(cam, p)
+    assert st.extend_variant == 2                  # one plain Bvh of spheres -> wf_extend_solo
+    for env in ({"SHIM_NO_GRAPH": "1"}, {"SHIM_SOLO": "0"}, {"SHIM_SOLO": "768", "SHIM_SOLO_ANY": "1"}, {"SHIM_TAIL": "0"},
+                {"SHIM_SOLO": "0", "SHIM_NO_GRAPH": "1", "SHIM_TAIL": "0"}):
+        img, st2 = _render_with_env(g, cam, p, env)
+        assert st2.rays == st.rays, env
+        if env.get("SHIM_SOLO") == "0":
+            assert st2.extend_variant == 0
+        np.testing.assert_allclose(img, ref, rtol=2e-5, atol=2e-6, err_msg=str(env))
+
+
+def test_page_locked_framebuffer_path_matches_staged_path():
+    g, o, info = build_pair("cornell-smoke")
+    cam = CAMERAS["cornell-smoke"]
+    p = api.make_params(96, 96, 4, 50, background=info.background, seed=9, pool_paths=1 << 16)
+    staged, st = g.render(cam, p)                  # pageable numpy buffer -> pinned staging + host copies
+    fb = api.HostFramebuffer(96, 96)               # shim_host_alloc -> one direct D2H
+    direct, st2 = g.render(cam, p, out=fb.array)
+    assert st2.rays == st.rays
+    np.testing.assert_allclose(np.array(direct), staged, rtol=2e-5, atol=2e-6)
+    fb.close()
