@@ -264,7 +264,7 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         w.grid_shade = sms * (per_sm > 0 ? per_sm : 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
         w.grid_generate = sms * (per_sm > 0 ? per_sm : 1);
-        w.grid_tail = sms * 2;
+        w.grid_tail = sms * 4;   // 128-thread blocks, one path per thread: covers the 65536-path trigger in one wave
         CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
@@ -434,7 +434,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         k.solo = spheres_only ? 896 : 768;   // 72 / 80 registers, no spills (measured: 3.15 / 3.21 ms on Book-1, 3.56 ms with wf_extend)
         if (const char* e = getenv("SHIM_SOLO")) k.solo = atoi(e);
     }
-    k.tail_threshold = 32768;
+    k.tail_threshold = 65536;   // measured on Book-1: 32 k 3.40 ms, 48 k 3.38, 64 k 3.35, 96 k 3.48 (the grid covers 75 k paths)
     if (const char* e = getenv("SHIM_TAIL")) k.tail_threshold = (uint32_t)atoi(e);
 
     CU(cudaMemsetAsync(w.cnt.p, 0, CNT_WORDS * sizeof(uint32_t), st));
