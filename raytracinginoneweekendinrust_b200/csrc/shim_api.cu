@@ -264,7 +264,11 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         w.grid_shade = sms * (per_sm > 0 ? per_sm : 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
         w.grid_generate = sms * (per_sm > 0 ? per_sm : 1);
-        w.grid_tail = sms * 4;   // 128-thread blocks, one path per thread: covers the 65536-path trigger in one wave
+        w.grid_tail = sms * 4;
+#define SHIM_LIST_ATTR(T) CU(cudaFuncSetAttribute(wf_extend_list<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
+                          CU(cudaFuncSetAttribute(wf_extend_list<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
+        SHIM_LIST_ATTR(640); SHIM_LIST_ATTR(768); SHIM_LIST_ATTR(896); SHIM_LIST_ATTR(1024);
+#undef SHIM_LIST_ATTR   // 128-thread blocks, one path per thread: covers the 65536-path trigger in one wave
         CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
@@ -293,6 +297,17 @@ static void launch_extend(const WfParams& k, int grid, uint32_t smem, cudaStream
         const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES;
         if (S) { if (C) wf_extend_bvh1<true, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<true, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
         else   { if (C) wf_extend_bvh1<false, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<false, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
+        return;
+    }
+    if (k.list_threads) {   // no Bvh in the world, scene image in shared memory
+#define SHIM_LIST_T(T) do { if (k.has_media) wf_extend_list<true, T><<<grid, T, smem, st>>>(); else wf_extend_list<false, T><<<grid, T, smem, st>>>(); } while (0)
+        switch (k.list_threads) {
+        case 640: SHIM_LIST_T(640); break;
+        case 768: SHIM_LIST_T(768); break;
+        case 896: SHIM_LIST_T(896); break;
+        default: SHIM_LIST_T(1024); break;
+        }
+#undef SHIM_LIST_T
         return;
     }
     if (k.solo) {   // one plain Bvh, scene image in shared memory
@@ -341,7 +356,7 @@ enum { SHIM_CHUNK = 4 };  // iterations per done-flag readback of the host-drive
 static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
     uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
                    ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
-                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48) | ((uint64_t)(k.solo && k.solo_only == PT_SPHERE) << 39);
+                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48) | ((uint64_t)(k.solo && k.solo_only == PT_SPHERE) << 39) | ((uint64_t)((uint32_t)k.list_threads / 128u) << 60);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));
@@ -434,6 +449,11 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         k.solo = spheres_only ? 896 : 768;   // 72 / 80 registers, no spills (measured: 3.15 / 3.21 ms on Book-1, 3.56 ms with wf_extend)
         if (const char* e = getenv("SHIM_SOLO")) k.solo = atoi(e);
     }
+    k.list_threads = 0;
+    if (use_smem && !k.count_nodes && !k.use_hrpp && s->flat.nodes.empty() && !k.solo) {
+        k.list_threads = 1024;   // cornell-smoke, 64 spp: 18.3 ms with wf_extend, 16.4 / 15.4 / 15.0 / 14.9 ms at 640 / 768 / 896 / 1024 threads
+        if (const char* e = getenv("SHIM_LIST")) k.list_threads = atoi(e);
+    }
     k.tail_threshold = 65536;   // measured on Book-1: 32 k 3.40 ms, 48 k 3.38, 64 k 3.35, 96 k 3.48 (the grid covers 75 k paths)
     if (const char* e = getenv("SHIM_TAIL")) k.tail_threshold = (uint32_t)atoi(e);
 
@@ -504,7 +524,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         stats->hrpp_false_positive = c64[C64_HRPP_FP];
         stats->hrpp_no_prediction = c64[C64_HRPP_NONE];
         stats->iterations = w.h_flags[32 + CNT_ITER];
-        stats->extend_variant = k.solo ? 2u : (k.bvh1_index >= 0 ? 1u : 0u);
+        stats->extend_variant = k.solo ? 2u : (k.list_threads ? 3u : (k.bvh1_index >= 0 ? 1u : 0u));
         // four kernels per executed iteration body (the last body may find the queue already empty) + wf_finalize
         stats->kernel_launches = 4ull * w.h_flags[32 + CNT_BODIES] + 1ull;
         float ms = 0;

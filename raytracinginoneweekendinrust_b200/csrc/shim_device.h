@@ -563,10 +563,11 @@ SHIM_HD bool bvh_closest_predicted(const SceneView& sv, const DevObject& ob, con
 }
 
 // shape of one top-level object against its object-space ray
-template <bool COUNT, bool HRPP>
+// HASBVH = false: the caller knows the world holds no Bvh object (a flat list like the Cornell scenes)
+template <bool COUNT, bool HRPP, bool HASBVH = true>
 SHIM_HD bool shape_hit(const SceneView& sv, const DevObject& ob, const RayCtx& c, float t_min, float t_max, float& t, uint32_t& prim,
                        int& face, TraceCounters* cnt) {
-    if (ob.kind == OBJ_PRIM) {
+    if (!HASBVH || ob.kind == OBJ_PRIM) {
         face = 0;
         if (COUNT) cnt->prims++;
         if (hit_prim(sv, (uint32_t)ob.ref, c, t_min, t_max, t, face)) { prim = (uint32_t)ob.ref; return true; }
@@ -581,7 +582,7 @@ SHIM_HD bool shape_hit(const SceneView& sv, const DevObject& ob, const RayCtx& c
 
 // HittableList::hit over the flattened world (hittable.rs:100-118), with ConstantMedium::hit
 // (hittable.rs:177-233) for medium objects.  `rng` must be keyed to STAGE_INTERSECT.
-template <bool COUNT, bool HRPP = false>
+template <bool COUNT, bool HRPP = false, bool HASBVH = true>
 SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float t_max, Rng& rng, TraceCounters* cnt) {
     Hit h; h.t = t_max; h.obj = -1; h.prim = 0; h.face = 0;
     float closest = t_max;
@@ -589,12 +590,12 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
         const DevObject& ob = sv.objects[oi];
         RayCtx c;
         c.r = object_ray(ob, ray);
-        if (ob.kind == OBJ_BVH) make_ctx(c, c.r);  // reciprocals are only needed for box tests
+        if (HASBVH && ob.kind == OBJ_BVH) make_ctx(c, c.r);  // reciprocals are only needed for box tests
         float t; uint32_t prim; int face;
         if (ob.flags & OBJ_MEDIUM) {
             float t1, t2;
-            if (!shape_hit<COUNT, HRPP>(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, cnt)) continue;
-            if (!shape_hit<COUNT, HRPP>(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, cnt)) continue;
+            if (!shape_hit<COUNT, HRPP, HASBVH>(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, cnt)) continue;
+            if (!shape_hit<COUNT, HRPP, HASBVH>(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, cnt)) continue;
             if (t1 < t_min) t1 = t_min;
             if (t2 > closest) t2 = closest;
             if (t1 >= t2) continue;
@@ -606,7 +607,7 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
             t = t1 + hit_distance / ray_length;
             closest = t;
             h.t = t; h.obj = oi; h.prim = 0; h.face = 0;
-        } else if (shape_hit<COUNT, HRPP>(sv, ob, c, t_min, closest, t, prim, face, cnt)) {
+        } else if (shape_hit<COUNT, HRPP, HASBVH>(sv, ob, c, t_min, closest, t, prim, face, cnt)) {
             closest = t;
             h.t = t; h.obj = oi; h.prim = prim; h.face = face;
         }

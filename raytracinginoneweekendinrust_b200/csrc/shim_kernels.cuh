@@ -61,6 +61,7 @@ struct WfParams {
     float bg[3];
     uint64_t seed;
     int has_media, count_nodes, use_hrpp;
+    int list_threads; // > 0: the world has no Bvh: wf_extend_list with this many threads per block
     int solo_only;    // wf_extend_solo: the one primitive type of the Bvh (PT_*), or -1 when mixed
     int solo;         // > 0: the world is exactly one plain Bvh: wf_extend_solo with this many threads per block
     int bvh1_index;   // >= 0: the world is one BVH object (this one) among plain primitives, no medium: wf_extend_bvh1 applies
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(256) wf_generate() {
 }
 
 // ---------------------------------------------------------------------------- extend
-template <bool COUNT, bool MEDIA, bool HRPP, bool SOLO = false, int ONLY = -1>
+template <bool COUNT, bool MEDIA, bool HRPP, bool SOLO = false, int ONLY = -1, bool HASBVH = true>
 __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& sv, int cur, uint32_t n) {
     const uint32_t n_round = (n + 31u) & ~31u;
     const uint32_t lane = threadIdx.x & 31u;
@@ -199,7 +200,7 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
             }
             TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
             Hit h; h.obj = -1; h.t = 0; h.prim = 0; h.face = 0;
-            if (!poisoned) h = SOLO ? closest_hit_solo<COUNT, ONLY>(sv, r, 0.001f, SHIM_INF, &tc) : closest_hit<COUNT, HRPP>(sv, r, 0.001f, SHIM_INF, rng, &tc);
+            if (!poisoned) h = SOLO ? closest_hit_solo<COUNT, ONLY>(sv, r, 0.001f, SHIM_INF, &tc) : closest_hit<COUNT, HRPP, HASBVH>(sv, r, 0.001f, SHIM_INF, rng, &tc);
             nodes += tc.nodes; prims += tc.prims; h_tp += tc.hrpp_tp; h_fp += tc.hrpp_fp; h_none += tc.hrpp_none;
             if (poisoned) {
                 // path ends without a contribution
@@ -327,6 +328,20 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_solo() {
     __shared__ uint64_t bar;
     SceneView sv = stage_scene(p, smem, &bar);
     extend_rays<COUNT, false, false, true, ONLY>(p, sv, cur, n);
+}
+
+// wf_extend for worlds without any Bvh (flat lists like the Cornell scenes, main.rs:477-557): the tree walk and its
+// stack are compiled out, which frees registers for more resident warps.
+template <bool MEDIA, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) wf_extend_list() {
+    const WfParams& p = g_p;
+    const int cur = (int)p.cnt[CNT_CUR];
+    const uint32_t n = p.cnt[cur];
+    if (blockIdx.x * blockDim.x >= n) return;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    SceneView sv = stage_scene(p, smem, &bar);
+    extend_rays<false, MEDIA, false, false, -1, false>(p, sv, cur, n);
 }
 
 // ---------------------------------------------------------------------------- extend, one-BVH worlds
