@@ -268,7 +268,11 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
 #define SHIM_LIST_ATTR(T) CU(cudaFuncSetAttribute(wf_extend_list<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
                           CU(cudaFuncSetAttribute(wf_extend_list<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
         SHIM_LIST_ATTR(640); SHIM_LIST_ATTR(768); SHIM_LIST_ATTR(896); SHIM_LIST_ATTR(1024);
-#undef SHIM_LIST_ATTR   // 128-thread blocks, one path per thread: covers the 65536-path trigger in one wave
+#undef SHIM_LIST_ATTR
+#define SHIM_BVH1_ATTR(T) CU(cudaFuncSetAttribute(wf_extend_bvh1<true, false, T, PT_TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
+                          CU(cudaFuncSetAttribute(wf_extend_bvh1<false, false, T, PT_TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
+        SHIM_BVH1_ATTR(640); SHIM_BVH1_ATTR(768); SHIM_BVH1_ATTR(896); SHIM_BVH1_ATTR(1024);
+#undef SHIM_BVH1_ATTR   // 128-thread blocks, one path per thread: covers the 65536-path trigger in one wave
         CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
         CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
@@ -294,7 +298,20 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
 static void launch_extend(const WfParams& k, int grid, uint32_t smem, cudaStream_t st) {
     const bool S = smem != 0, C = k.count_nodes != 0, M = k.has_media != 0, H = k.use_hrpp != 0;
     if (k.bvh1_index >= 0) {  // one BVH among plain objects, no medium, no predictor: two-phase variant
-        const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES;
+        if (k.bvh1_tri_threads && !C) {   // triangle-only tree: no primitive dispatch, more warps
+            const int T = k.bvh1_tri_threads;
+            const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES_T(T);
+#define SHIM_BVH1_T(TT) do { if (S) wf_extend_bvh1<true, false, TT, PT_TRI><<<grid, TT, dyn, st>>>(); else wf_extend_bvh1<false, false, TT, PT_TRI><<<grid, TT, dyn, st>>>(); } while (0)
+            switch (T) {
+            case 640: SHIM_BVH1_T(640); break;
+            case 768: SHIM_BVH1_T(768); break;
+            case 896: SHIM_BVH1_T(896); break;
+            default: SHIM_BVH1_T(1024); break;
+            }
+#undef SHIM_BVH1_T
+            return;
+        }
+        const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES_T(SHIM_EXTEND_THREADS);
         if (S) { if (C) wf_extend_bvh1<true, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<true, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
         else   { if (C) wf_extend_bvh1<false, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<false, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
         return;
@@ -356,7 +373,7 @@ enum { SHIM_CHUNK = 4 };  // iterations per done-flag readback of the host-drive
 static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
     uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
                    ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
-                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48) | ((uint64_t)(k.solo && k.solo_only == PT_SPHERE) << 39) | ((uint64_t)((uint32_t)k.list_threads / 128u) << 60);
+                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48) | ((uint64_t)(k.solo && k.solo_only == PT_SPHERE) << 39) | ((uint64_t)((uint32_t)k.list_threads / 128u) << 60) | ((uint64_t)((uint32_t)k.bvh1_tri_threads / 128u) << 52);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));
@@ -448,6 +465,20 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         k.solo_only = spheres_only ? (int)PT_SPHERE : -1;
         k.solo = spheres_only ? 896 : 768;   // 72 / 80 registers, no spills (measured: 3.15 / 3.21 ms on Book-1, 3.56 ms with wf_extend)
         if (const char* e = getenv("SHIM_SOLO")) k.solo = atoi(e);
+    }
+    k.bvh1_tri_threads = 0;
+    if (k.bvh1_index >= 0 && s->flat.sph_s.empty() && s->flat.msph.empty() && s->flat.cube.empty() && !s->flat.tri.empty()) {
+        // plain objects are rects, so every primitive inside the Bvh is a triangle
+        bool rects_outside = true;
+        for (size_t i = 0; i < s->flat.objects.size(); ++i)
+            if ((int)i != k.bvh1_index && (s->flat.objects[i].kind != OBJ_PRIM || prim_type((uint32_t)s->flat.objects[i].ref) != PT_RECT)) rects_outside = false;
+        // ... and no rect inside it: every rect of the scene is a top-level object
+        size_t top_rects = 0;
+        for (const DevObject& o : s->flat.objects) if (o.kind == OBJ_PRIM) ++top_rects;
+        if (rects_outside && top_rects * 2 == s->flat.rect.size()) {
+            k.bvh1_tri_threads = 896;   // bunny / igea stand-ins: 43.8 / 70.7 ms generic, 39.7 / 62.9 ms at 896 threads (768: 40.9 / 65.9)
+            if (const char* e = getenv("SHIM_BVH1_TRI")) k.bvh1_tri_threads = atoi(e);
+        }
     }
     k.list_threads = 0;
     if (use_smem && !k.count_nodes && !k.use_hrpp && s->flat.nodes.empty() && !k.solo) {

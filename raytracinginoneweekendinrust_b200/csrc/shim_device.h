@@ -315,6 +315,7 @@ template <int ONLY = -1>
 SHIM_HD bool hit_prim(const SceneView& sv, uint32_t ref, const RayCtx& c, float t_min, float t_max, float& t, int& face) {
     uint32_t i = prim_index(ref);
     if (ONLY == PT_SPHERE) return hit_sphere(sv.sph + 4 * (size_t)i, c.r, t_min, t_max, t);
+    if (ONLY == PT_TRI) return hit_tri(sv.tri + 3 * (size_t)i, c.r, t_min, t_max, t);
     switch (prim_type(ref)) {
     case PT_SPHERE: return hit_sphere(sv.sph + 4 * (size_t)i, c.r, t_min, t_max, t);
     case PT_MSPHERE: return hit_msphere(sv.msph + 3 * (size_t)i, c.r, t_min, t_max, t);
@@ -432,7 +433,7 @@ SHIM_HD void bvh_walk_init(BvhWalk& w, int start_node, float t_max) {
 }
 SHIM_HD bool bvh_walk_done(const BvhWalk& w) { return w.cur == SHIM_STACK_END; }
 // advances to and through the next primitive test (or to the end of the walk)
-template <bool COUNT>
+template <bool COUNT, int ONLY = -1>
 SHIM_HD void bvh_walk_step(const SceneView& sv, BvhWalk& w, int* stack, const RayCtx& c, float t_min, TraceCounters* cnt) {
     while (w.cur >= 0 && w.cur != SHIM_STACK_END) {
         const DevNode& n = sv.nodes[w.cur];
@@ -459,9 +460,9 @@ SHIM_HD void bvh_walk_step(const SceneView& sv, BvhWalk& w, int* stack, const Ra
     uint32_t ref = ~(uint32_t)w.cur;
     float t; int face = 0;
     if (COUNT) cnt->prims++;
-    if (hit_prim(sv, ref, c, t_min, w.t_cull, t, face) && !(t > w.best.t)) {
+    if (hit_prim<ONLY>(sv, ref, c, t_min, w.t_cull, t, face) && !(t > w.best.t)) {
         bool take = !w.best.any || t < w.best.t;
-        if (!take) take = tie_goes_to_candidate(sv, c, t_min, ref, w.best.prim, t);
+        if (!take) take = tie_goes_to_candidate<ONLY>(sv, c, t_min, ref, w.best.prim, t);
         if (take) { w.best.t = t; w.best.prim = ref; w.best.face = face; w.best.any = true; w.t_cull = t + fabsf(t) * 3.8146973e-06f; }
     }
     w.cur = w.sp > 0 ? stack[--w.sp] : SHIM_STACK_END;

@@ -61,6 +61,7 @@ struct WfParams {
     float bg[3];
     uint64_t seed;
     int has_media, count_nodes, use_hrpp;
+    int bvh1_tri_threads;   // > 0: the one Bvh holds only triangles: wf_extend_bvh1<.., THREADS, PT_TRI>
     int list_threads; // > 0: the world has no Bvh: wf_extend_list with this many threads per block
     int solo_only;    // wf_extend_solo: the one primitive type of the Bvh (PT_*), or -1 when mixed
     int solo;         // > 0: the world is exactly one plain Bvh: wf_extend_solo with this many threads per block
@@ -387,7 +388,7 @@ __device__ __forceinline__ void bvh1_finish(const WfParams& p, const SceneView& 
     }
 }
 
-template <bool COUNT>
+template <bool COUNT, int ONLY = -1>
 __device__ __forceinline__ void extend_rays_bvh1(const WfParams& p, const SceneView& sv, int cur, uint32_t n, Bvh1Entry* entries_base) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5), warp_global = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -487,7 +488,7 @@ __device__ __forceinline__ void extend_rays_bvh1(const WfParams& p, const SceneV
             if (!__any_sync(0xffffffffu, active)) break;
             for (;;) {
                 if (active) {
-                    bvh_walk_step<COUNT>(sv, w, stack, c, 0.001f, &tc);
+                    bvh_walk_step<COUNT, ONLY>(sv, w, stack, c, 0.001f, &tc);
                     if (bvh_walk_done(w)) { active = false; pending = true; }
                 }
                 const unsigned act = __ballot_sync(0xffffffffu, active);
@@ -508,8 +509,8 @@ __device__ __forceinline__ void extend_rays_bvh1(const WfParams& p, const SceneV
     }
 }
 
-template <bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend_bvh1() {
+template <bool SMEM, bool COUNT, int THREADS = SHIM_EXTEND_THREADS, int ONLY = -1>
+__global__ void __launch_bounds__(THREADS, 1) wf_extend_bvh1() {
     const WfParams& p = g_p;
     const int cur = (int)p.cnt[CNT_CUR];
     const uint32_t n = p.cnt[cur];
@@ -542,9 +543,10 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend_bvh1() {
         sv.sph_mat = reinterpret_cast<const int*>(smem + p.smem.off_sph_mat);
         mbar_wait(&bar, 0);
     }
-    extend_rays_bvh1<COUNT>(p, sv, cur, n, reinterpret_cast<Bvh1Entry*>(smem + (SMEM ? p.smem.total : 0u)));
+    extend_rays_bvh1<COUNT, ONLY>(p, sv, cur, n, reinterpret_cast<Bvh1Entry*>(smem + (SMEM ? p.smem.total : 0u)));
 }
-#define SHIM_BVH1_SMEM_BYTES ((SHIM_EXTEND_THREADS / 32) * SHIM_BVH1_GROUP * 32 * (int)sizeof(Bvh1Entry))
+#define SHIM_BVH1_SMEM_BYTES_T(T) (((T) / 32) * SHIM_BVH1_GROUP * 32 * (int)sizeof(Bvh1Entry))
+#define SHIM_BVH1_SMEM_BYTES SHIM_BVH1_SMEM_BYTES_T(1024)   /* reserved for the largest block variant */
 
 // ---------------------------------------------------------------------------- shade
 struct ShadeOut { bool cont; Ray ray; f3 thr; };
