@@ -1,7 +1,7 @@
 // shim_kernels.cuh — sm_100a wavefront kernels.
 //
 // One iteration of the wavefront (replaces the per-tile loop of renderer.rs:63-85 and the
-// recursion of ray.rs:32-62) is three launches:
+// recursion of ray.rs:32-62) is four launches:
 //
 //   wf_generate  tops the current ray queue up with camera rays for new samples
 //                (renderer.rs:141-143, camera.rs:96-106); the last block to finish advances the
@@ -16,12 +16,15 @@
 //                256-ray chunk of a queue is streamed (coalesced) through code specialised for
 //                that material: rebuild the HitRecord, emit, scatter, and append the continuing
 //                ray to the next ray queue (warp-ballot compaction, one atomic per warp)
-//   wf_tail      once no samples are left to start and only a few thousand paths are alive, one
-//                launch finishes them (extend + shade in a loop per thread) instead of ~40
-//                near-empty iterations
+//                (wf_extend_solo / wf_extend_list / wf_extend_bvh1: the same walk with what a
+//                scene cannot need compiled out - fewer registers, more resident warps)
+//   wf_tail      once no samples are left to start and at most 65536 paths are alive, one
+//                launch finishes them (extend + shade in a loop per thread) instead of ~35
+//                near-empty iterations; it also decides whether the loop goes on
 //
-// Ray queues are SoA float4 streams in HBM, double buffered; all counts live on the device,
-// the host only polls a done flag every few iterations.
+// Ray queues are SoA float4 streams in HBM, double buffered; all counts, the queue index and
+// the termination test live on the device: the iteration is the body of a CUDA-graph WHILE
+// node, so the host launches one graph per render and never polls.
 #pragma once
 #include <cuda_runtime.h>
 #include "shim_device.h"
