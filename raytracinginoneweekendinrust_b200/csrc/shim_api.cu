@@ -370,6 +370,16 @@ static void launch_iteration(const Wavefront& w, const WfParams& k, bool use_sme
 // internal stream.
 enum { SHIM_CHUNK = 4 };  // iterations per done-flag readback of the host-driven loop
 
+// Nsight Compute cannot profile kernel nodes of a graph that contains conditional nodes ("not supported for profiling"),
+// and other CUPTI-injection tools may not list them either: when the process runs under such a tool the very same
+// kernels are launched by the host-driven loop instead, so that every launch stays visible.
+static bool under_profiler() {
+    static const char* const marks[] = {"NV_COMPUTE_PROFILER_PERFWORKS_DIR", "CUDA_INJECTION64_PATH", "NV_TPS_LAUNCH_TOKEN",
+                                        "NVIDIA_PROCESS_INJECTION_CRASH_REPORTING", "NSYS_PROFILING_SESSION_ID"};
+    for (const char* m : marks) if (getenv(m)) return true;
+    return false;
+}
+
 static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
     uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
                    ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
@@ -503,7 +513,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     k.max_iterations = 1u << 30;
     const bool run = k.total_samples > 0 && p.max_depth > 0;
     // Without per-kernel events the loop is ONE graph launch (WHILE node, condition set by wf_tail on the device).
-    const bool use_graph = run && !profile && !getenv("SHIM_NO_GRAPH");
+    const bool use_graph = run && !profile && !getenv("SHIM_NO_GRAPH") && !under_profiler();
     Wavefront::LoopGraph lg{nullptr, 0ull};
     if (use_graph) { int grc = loop_graph(w, k, use_smem, &lg); if (grc < 0) return grc; }
     k.loop_handle = lg.handle;
