@@ -273,14 +273,22 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
                           CU(cudaFuncSetAttribute(wf_extend_bvh1<false, false, T, PT_TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
         SHIM_BVH1_ATTR(640); SHIM_BVH1_ATTR(768); SHIM_BVH1_ATTR(896); SHIM_BVH1_ATTR(1024);
 #undef SHIM_BVH1_ATTR   // 128-thread blocks, one path per thread: covers the 65536-path trigger in one wave
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, PT_SPHERE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, PT_SPHERE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, PT_SPHERE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, PT_SPHERE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, PT_SPHERE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, PT_SPHERE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, PT_SPHERE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
+        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, PT_SPHERE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
     }
     size_t fb = (size_t)p.width * p.height * 3;
     if (w.accum.n != fb) CU(w.accum.alloc(fb));
@@ -328,8 +336,10 @@ static void launch_extend(const WfParams& k, int grid, uint32_t smem, cudaStream
         return;
     }
     if (k.solo) {   // one plain Bvh, scene image in shared memory
-#define SHIM_SOLO_T(T) do { if (k.solo_only == PT_SPHERE) wf_extend_solo<false, T, PT_SPHERE><<<grid, T, smem, st>>>(); \
-                            else wf_extend_solo<false, T, -1><<<grid, T, smem, st>>>(); } while (0)
+#define SHIM_SOLO_T(T) do { if (k.solo_only == PT_SPHERE) { if (k.fused_generate) wf_extend_solo<false, T, PT_SPHERE, true><<<grid, T, smem, st>>>(); \
+                                                           else wf_extend_solo<false, T, PT_SPHERE, false><<<grid, T, smem, st>>>(); } \
+                            else { if (k.fused_generate) wf_extend_solo<false, T, -1, true><<<grid, T, smem, st>>>(); \
+                                   else wf_extend_solo<false, T, -1, false><<<grid, T, smem, st>>>(); } } while (0)
         switch (k.solo) {
         case 640: SHIM_SOLO_T(640); break;
         case 768: SHIM_SOLO_T(768); break;
@@ -383,7 +393,7 @@ static bool under_profiler() {
 static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
     uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
                    ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
-                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48) | ((uint64_t)(k.solo && k.solo_only == PT_SPHERE) << 39) | ((uint64_t)((uint32_t)k.list_threads / 128u) << 60) | ((uint64_t)((uint32_t)k.bvh1_tri_threads / 128u) << 52);
+                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48) | ((uint64_t)(k.solo && k.solo_only == PT_SPHERE) << 39) | ((uint64_t)((uint32_t)k.list_threads / 128u) << 60) | ((uint64_t)(k.fused_generate != 0) << 38) | ((uint64_t)((uint32_t)k.bvh1_tri_threads / 128u) << 52);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));
@@ -475,6 +485,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         k.solo_only = spheres_only ? (int)PT_SPHERE : -1;
         k.solo = spheres_only ? 896 : 768;   // 72 / 80 registers, no spills (measured: 3.15 / 3.21 ms on Book-1, 3.56 ms with wf_extend)
         if (const char* e = getenv("SHIM_SOLO")) k.solo = atoi(e);
+        k.fused_generate = (k.solo && !getenv("SHIM_NO_FUSE")) ? 1 : 0;
     }
     k.bvh1_tri_threads = 0;
     if (k.bvh1_index >= 0 && s->flat.sph_s.empty() && s->flat.msph.empty() && s->flat.cube.empty() && !s->flat.tri.empty()) {

@@ -32,8 +32,8 @@
 namespace shim {
 
 enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..6 */, CNT_CUR = 7, CNT_TICKET = 8, CNT_NEXT_CUR = 9, CNT_DONE = 10, CNT_ITER = 11,
-       CNT_BODIES = 12 /* iteration bodies executed */, CNT_U64_BASE = 14 /* u64 slots from here, as pairs */ };
-enum { C64_NEXT_SAMPLE = 0, C64_RAYS = 1, C64_NODES = 2, C64_PRIMS = 3, C64_HRPP_TP = 4, C64_HRPP_FP = 5, C64_HRPP_NONE = 6, C64_COUNT = 7 };
+       CNT_BODIES = 12 /* iteration bodies executed */, CNT_GEN_BASE = 13 /* fused generation: queue slot of the first new sample */, CNT_U64_BASE = 14 /* u64 slots from here, as pairs */ };
+enum { C64_NEXT_SAMPLE = 0, C64_RAYS = 1, C64_NODES = 2, C64_PRIMS = 3, C64_HRPP_TP = 4, C64_HRPP_FP = 5, C64_HRPP_NONE = 6, C64_GEN_FIRST = 7, C64_COUNT = 8 };
 enum { CNT_WORDS = CNT_U64_BASE + 2 * C64_COUNT };
 
 // shared-memory image of the scene arrays wf_extend walks (byte offsets, all multiples of 16)
@@ -66,6 +66,7 @@ struct WfParams {
     int has_media, count_nodes, use_hrpp;
     int bvh1_tri_threads;   // > 0: the one Bvh holds only triangles: wf_extend_bvh1<.., THREADS, PT_TRI>
     int list_threads; // > 0: the world has no Bvh: wf_extend_list with this many threads per block
+    int fused_generate;   // wf_generate only publishes the counters; wf_extend_solo makes the camera rays itself
     int solo_only;    // wf_extend_solo: the one primitive type of the Bvh (PT_*), or -1 when mixed
     int solo;         // > 0: the world is exactly one plain Bvh: wf_extend_solo with this many threads per block
     int bvh1_index;   // >= 0: the world is one BVH object (this one) among plain primitives, no medium: wf_extend_bvh1 applies
@@ -123,6 +124,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// the ray record of global sample index g (renderer.rs:140-146): pixel from the tile-ordered table, Philox stage 0
+__device__ __forceinline__ void camera_ray_record(const WfParams& p, unsigned long long g, f4& o, f4& d, f4& t) {
+    uint32_t s, pi;
+    if (p.total_samples <= 0xffffffffull) { s = (uint32_t)g / p.npix; pi = (uint32_t)g - s * p.npix; }   // 32-bit divide when it fits
+    else { s = (uint32_t)(g / p.npix); pi = (uint32_t)(g - (unsigned long long)s * p.npix); }
+    const uint32_t pixel = p.pix_table[pi];
+    const int x = (int)(pixel % (uint32_t)p.width), y = (int)(pixel / (uint32_t)p.width);
+    const uint32_t sample = (uint32_t)p.sample_begin + s;
+    Rng rng;
+    rng_init(rng, pixel, sample, p.seed);
+    rng_key(rng, 0, STAGE_CAMERA);
+    const Ray r = camera_sample(p.cam, x, y, p.width, p.height, rng);
+    o.x = r.o.x; o.y = r.o.y; o.z = r.o.z; o.w = r.time;
+    d.x = r.d.x; d.y = r.d.y; d.z = r.d.z; d.w = i2f((int)(sample << 8));
+    t.x = 1.0f; t.y = 1.0f; t.z = 1.0f; t.w = i2f((int)pixel);
+}
+
 // ---------------------------------------------------------------------------- generate
 // All blocks read the pre-iteration counters, write their camera rays, and the last block to
 // finish (ticket) publishes the counters the rest of the iteration uses.
@@ -135,25 +153,15 @@ __global__ void __launch_bounds__(256) wf_generate() {
     const unsigned long long remaining = p.total_samples - first;
     const unsigned long long room = (unsigned long long)(p.pool - n_cur);
     const uint32_t n = (uint32_t)(remaining < room ? remaining : room);
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        unsigned long long g = first + j;
-        uint32_t s, pi;
-        if (p.total_samples <= 0xffffffffull) { s = (uint32_t)g / p.npix; pi = (uint32_t)g - s * p.npix; }   // 32-bit divide when it fits
-        else { s = (uint32_t)(g / p.npix); pi = (uint32_t)(g - (unsigned long long)s * p.npix); }
-        uint32_t pixel = p.pix_table[pi];
-        int x = (int)(pixel % (uint32_t)p.width), y = (int)(pixel / (uint32_t)p.width);
-        uint32_t sample = (uint32_t)p.sample_begin + s;
-        Rng rng;
-        rng_init(rng, pixel, sample, p.seed);
-        rng_key(rng, 0, STAGE_CAMERA);
-        Ray r = camera_sample(p.cam, x, y, p.width, p.height, rng);
-        uint32_t slot = n_cur + j;
-        f4 o; o.x = r.o.x; o.y = r.o.y; o.z = r.o.z; o.w = r.time;
-        f4 d; d.x = r.d.x; d.y = r.d.y; d.z = r.d.z; d.w = i2f((int)(sample << 8));
-        f4 t; t.x = 1.0f; t.y = 1.0f; t.z = 1.0f; t.w = i2f((int)pixel);
-        p.ray_o[cur][slot] = o;
-        p.ray_d[cur][slot] = d;
-        p.thr[cur][slot] = t;
+    if (!p.fused_generate) {
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+            f4 o, d, t;
+            camera_ray_record(p, first + j, o, d, t);
+            const uint32_t slot = n_cur + j;
+            p.ray_o[cur][slot] = o;
+            p.ray_d[cur][slot] = d;
+            p.thr[cur][slot] = t;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -164,6 +172,8 @@ __global__ void __launch_bounds__(256) wf_generate() {
             c[CNT_CUR] = (uint32_t)cur;            // the queue the rest of this iteration works on
             c[CNT_NEXT_CUR] = (uint32_t)(1 - cur);
             *cnt64(c, C64_NEXT_SAMPLE) = first + n;
+            c[CNT_GEN_BASE] = n_cur;               // fused generation: queue slots n_cur .. n_cur + n - 1 are samples first ..
+            *cnt64(c, C64_GEN_FIRST) = first;
             c[cur] = n_cur + n;
             c[1 - cur] = 0;
 #pragma unroll
@@ -177,16 +187,21 @@ __global__ void __launch_bounds__(256) wf_generate() {
 }
 
 // ---------------------------------------------------------------------------- extend
-template <bool COUNT, bool MEDIA, bool HRPP, bool SOLO = false, int ONLY = -1, bool HASBVH = true>
+template <bool COUNT, bool MEDIA, bool HRPP, bool SOLO = false, int ONLY = -1, bool HASBVH = true, bool FUSE = false>
 __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& sv, int cur, uint32_t n) {
     const uint32_t n_round = (n + 31u) & ~31u;
+    // FUSE: queue slots from gen_base on are new samples whose camera rays are made here instead of being written by
+    // wf_generate and read back (96 B of HBM traffic per sample)
+    const uint32_t gen_base = FUSE ? p.cnt[CNT_GEN_BASE] : 0xffffffffu;
+    const unsigned long long gen_first = FUSE ? *cnt64(p.cnt, C64_GEN_FIRST) : 0ull;
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t nodes = 0, prims = 0, h_tp = 0, h_fp = 0, h_none = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         int kind = 7;
         f4 o, d, t, hv;
         if (i < n) {
-            o = p.ray_o[cur][i]; d = p.ray_d[cur][i]; t = p.thr[cur][i];
+            if (FUSE && i >= gen_base) camera_ray_record(p, gen_first + (i - gen_base), o, d, t);
+            else { o = p.ray_o[cur][i]; d = p.ray_d[cur][i]; t = p.thr[cur][i]; }
             Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
             // A ray with a NaN component (born as t = 0/0 in a rect test, rectangle.rs:44, when a ray starts on the
             // rect's plane with an exactly zero direction component) fails no comparison: in the reference it "hits"
@@ -322,7 +337,7 @@ __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
 
 // The same kernel for worlds that are one plain Bvh and nothing else (Book-1): closest_hit_solo needs fewer registers,
 // so more warps are resident to cover the walk's dependent latencies.
-template <bool COUNT, int THREADS, int ONLY>
+template <bool COUNT, int THREADS, int ONLY, bool FUSE = false>
 __global__ void __launch_bounds__(THREADS, 1) wf_extend_solo() {
     const WfParams& p = g_p;
     const int cur = (int)p.cnt[CNT_CUR];
@@ -331,7 +346,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_solo() {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     SceneView sv = stage_scene(p, smem, &bar);
-    extend_rays<COUNT, false, false, true, ONLY>(p, sv, cur, n);
+    extend_rays<COUNT, false, false, true, ONLY, true, FUSE>(p, sv, cur, n);
 }
 
 // wf_extend for worlds without any Bvh (flat lists like the Cornell scenes, main.rs:477-557): the tree walk and its

@@ -129,14 +129,14 @@ def _render_with_env(g, cam, params, env, out=None):
 
 
 def test_kernel_variants_agree():
-    """The device-side WHILE-node loop vs the host-driven loop, wf_extend_solo vs the generic wf_extend and wf_tail
-    vs plain iterations trace the same rays and give the same image (radiance sums differ only in atomicAdd order)."""
+    """The device-side WHILE-node loop vs the host-driven loop, camera rays made inside wf_extend_solo vs written by
+    wf_generate, wf_extend_solo vs the generic wf_extend and wf_tail vs plain iterations trace the same rays and give the same image (radiance sums differ only in atomicAdd order)."""
     g, o, info = build_pair("random-spheres")
     cam = CAMERAS["random-spheres"]
     p = api.make_params(192, 128, 6, 50, background=info.background, seed=5)
     ref, st = g.render(cam, p)
     assert st.extend_variant == 2                  # one plain Bvh of spheres -> wf_extend_solo
-    for env in ({"SHIM_NO_GRAPH": "1"}, {"SHIM_SOLO": "0"}, {"SHIM_SOLO": "768", "SHIM_SOLO_ANY": "1"}, {"SHIM_TAIL": "0"},
+    for env in ({"SHIM_NO_GRAPH": "1"}, {"SHIM_NO_FUSE": "1"}, {"SHIM_SOLO": "0"}, {"SHIM_SOLO": "768", "SHIM_SOLO_ANY": "1"}, {"SHIM_TAIL": "0"},
                 {"SHIM_SOLO": "0", "SHIM_NO_GRAPH": "1", "SHIM_TAIL": "0"}):
         img, st2 = _render_with_env(g, cam, p, env)
         assert st2.rays == st.rays, env
