@@ -139,7 +139,7 @@ typedef struct shim_stats {
     double device_ms;              /* CUDA events around the wavefront loop */
     double extend_ms, shade_ms, generate_ms; /* event sums per kernel class (extend only, with SHIM_RENDER_PROFILE) */
     uint64_t extend_launches;      /* wf_extend launches that had rays, covered by extend_ms */
-    uint64_t extend_variant;       /* which closest-hit kernel ran: 0 wf_extend, 1 wf_extend_bvh1, 2 wf_extend_solo, 3 wf_extend_list */
+    uint64_t extend_variant;       /* which closest-hit kernel ran: 0 wf_extend, 1 wf_extend_bvh1, 2 wf_extend_solo, 3 wf_extend_list, 4 wf_trace_solo */
 } shim_stats;
 
 /* host framebuffer: width*height*3 floats, linear radiance, row-major, y = 0 is the bottom row

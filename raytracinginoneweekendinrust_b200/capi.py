@@ -78,7 +78,7 @@ class Stats(C.Structure):
         ("extend_variant", C.c_uint64),
     ]
 
-    EXTEND_KERNELS = {0: "wf_extend", 1: "wf_extend_bvh1", 2: "wf_extend_solo", 3: "wf_extend_list"}
+    EXTEND_KERNELS = {0: "wf_extend", 1: "wf_extend_bvh1", 2: "wf_extend_solo", 3: "wf_extend_list", 4: "wf_trace_solo"}
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

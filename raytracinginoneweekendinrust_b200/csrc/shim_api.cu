@@ -239,10 +239,11 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
     pool = (pool + 31u) & ~31u;
     if (w.pool != pool) {
         for (int i = 0; i < 2; ++i) { CU(w.ray_o[i].alloc(pool)); CU(w.ray_d[i].alloc(pool)); CU(w.thr[i].alloc(pool)); }
-        CU(w.mq_o.alloc((size_t)pool * MAT_KINDS)); CU(w.mq_d.alloc((size_t)pool * MAT_KINDS));
-        CU(w.mq_thr.alloc((size_t)pool * MAT_KINDS)); CU(w.mq_hit.alloc((size_t)pool * MAT_KINDS));
+        // two sets of material queues: the wf_trace pipeline goes from one set to the other (the wavefront pipeline uses set 0)
+        CU(w.mq_o.alloc((size_t)pool * MAT_KINDS * 2)); CU(w.mq_d.alloc((size_t)pool * MAT_KINDS * 2));
+        CU(w.mq_thr.alloc((size_t)pool * MAT_KINDS * 2)); CU(w.mq_hit.alloc((size_t)pool * MAT_KINDS * 2));
         CU(w.cnt.alloc(CNT_WORDS));
-        if (!w.h_flags) CU(cudaMallocHost(&w.h_flags, 64 * sizeof(uint32_t)));
+        if (!w.h_flags) CU(cudaMallocHost(&w.h_flags, 128 * sizeof(uint32_t)));
         if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); CU(cudaEventCreate(&w.ev_chunk[0])); CU(cudaEventCreate(&w.ev_chunk[1])); }
         w.pool = pool;
         int sms = s->dev->sm_count, per_sm = 0;
@@ -265,6 +266,10 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
         w.grid_generate = sms * (per_sm > 0 ? per_sm : 1);
         w.grid_tail = sms * 4;
+#define SHIM_TRACE_ATTR(T) CU(cudaFuncSetAttribute(wf_trace_solo<T, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
+                           CU(cudaFuncSetAttribute(wf_trace_solo<T, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
+        SHIM_TRACE_ATTR(512); SHIM_TRACE_ATTR(640); SHIM_TRACE_ATTR(768); SHIM_TRACE_ATTR(896);
+#undef SHIM_TRACE_ATTR
 #define SHIM_LIST_ATTR(T) CU(cudaFuncSetAttribute(wf_extend_list<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
                           CU(cudaFuncSetAttribute(wf_extend_list<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
         SHIM_LIST_ATTR(640); SHIM_LIST_ATTR(768); SHIM_LIST_ATTR(896); SHIM_LIST_ATTR(1024);
@@ -368,7 +373,28 @@ static void launch_tail(const Wavefront& w, const WfParams& k, cudaStream_t st) 
     }
     if (k.use_hrpp) wf_tail<true><<<w.grid_tail, 128, 0, st>>>(); else wf_tail<false><<<w.grid_tail, 128, 0, st>>>();
 }
+static void launch_trace(const Wavefront& w, const WfParams& k, cudaStream_t st) {
+    const int grid = w.grid_extend_smem;
+    const uint32_t smem = k.smem.total;
+#define SHIM_TRACE_T(T) do { if (k.solo_only == PT_SPHERE) wf_trace_solo<T, PT_SPHERE><<<grid, T, smem, st>>>(); else wf_trace_solo<T, -1><<<grid, T, smem, st>>>(); } while (0)
+    switch (k.trace_pipeline) {
+    case 512: SHIM_TRACE_T(512); break;
+    case 640: SHIM_TRACE_T(640); break;
+    case 768: SHIM_TRACE_T(768); break;
+    default: SHIM_TRACE_T(896); break;
+    }
+#undef SHIM_TRACE_T
+}
+static void launch_tail_mq(const Wavefront& w, const WfParams& k, cudaStream_t st) {
+    if (k.solo_only == PT_SPHERE) wf_tail_mq<PT_SPHERE><<<w.grid_tail, 128, 0, st>>>(); else wf_tail_mq<-1><<<w.grid_tail, 128, 0, st>>>();
+}
 static void launch_iteration(const Wavefront& w, const WfParams& k, bool use_smem, cudaStream_t st) {
+    if (k.trace_pipeline) {   // counters, shade -> closest hit, endgame / loop condition
+        wf_generate<<<w.grid_generate, 256, 0, st>>>();
+        launch_trace(w, k, st);
+        launch_tail_mq(w, k, st);
+        return;
+    }
     wf_generate<<<w.grid_generate, 256, 0, st>>>();
     launch_extend(k, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
     wf_shade<<<w.grid_shade, 256, 0, st>>>();
@@ -393,7 +419,7 @@ static bool under_profiler() {
 static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
     uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
                    ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
-                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48) | ((uint64_t)(k.solo && k.solo_only == PT_SPHERE) << 39) | ((uint64_t)((uint32_t)k.list_threads / 128u) << 60) | ((uint64_t)(k.fused_generate != 0) << 38) | ((uint64_t)((uint32_t)k.bvh1_tri_threads / 128u) << 52);
+                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48) | ((uint64_t)(k.solo && k.solo_only == PT_SPHERE) << 39) | ((uint64_t)((uint32_t)k.list_threads / 128u) << 60) | ((uint64_t)(k.fused_generate != 0) << 38) | ((uint64_t)((uint32_t)k.trace_pipeline / 128u) << 44) | ((uint64_t)((uint32_t)k.bvh1_tri_threads / 128u) << 52);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));
@@ -486,6 +512,11 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         k.solo = spheres_only ? 896 : 768;   // 72 / 80 registers, no spills (measured: 3.15 / 3.21 ms on Book-1, 3.56 ms with wf_extend)
         if (const char* e = getenv("SHIM_SOLO")) k.solo = atoi(e);
         k.fused_generate = (k.solo && !getenv("SHIM_NO_FUSE")) ? 1 : 0;
+        if (k.solo && !getenv("SHIM_NO_TRACE")) {
+            k.trace_pipeline = 896;   // Book-1: 3.00 ms wavefront, 3.28 / 3.00 / 2.92 / 2.91 ms at 512 / 640 / 768 / 896 threads
+            if (const char* e = getenv("SHIM_TRACE_T")) k.trace_pipeline = atoi(e);
+            if (k.trace_pipeline) k.fused_generate = 1;   // wf_generate only publishes counters in this pipeline
+        }
     }
     k.bvh1_tri_threads = 0;
     if (k.bvh1_index >= 0 && s->flat.sph_s.empty() && s->flat.msph.empty() && s->flat.cube.empty() && !s->flat.tri.empty()) {
@@ -542,10 +573,11 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
                 if (rec) CU(cudaEventRecord(w.prof[prof_used], st));
                 wf_generate<<<w.grid_generate, 256, 0, st>>>();
                 if (rec) CU(cudaEventRecord(w.prof[prof_used + 1], st));
-                launch_extend(k, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
+                if (k.trace_pipeline) launch_trace(w, k, st);
+                else launch_extend(k, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
                 if (rec) CU(cudaEventRecord(w.prof[prof_used + 2], st));
-                wf_shade<<<w.grid_shade, 256, 0, st>>>();
-                launch_tail(w, k, st);
+                if (k.trace_pipeline) launch_tail_mq(w, k, st);
+                else { wf_shade<<<w.grid_shade, 256, 0, st>>>(); launch_tail(w, k, st); }
                 if (rec) { CU(cudaEventRecord(w.prof[prof_used + 3], st)); prof_used += 4; }
             }
             int slot = c & 1;
@@ -576,9 +608,9 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         stats->hrpp_false_positive = c64[C64_HRPP_FP];
         stats->hrpp_no_prediction = c64[C64_HRPP_NONE];
         stats->iterations = w.h_flags[32 + CNT_ITER];
-        stats->extend_variant = k.solo ? 2u : (k.list_threads ? 3u : (k.bvh1_index >= 0 ? 1u : 0u));
+        stats->extend_variant = k.trace_pipeline ? 4u : k.solo ? 2u : (k.list_threads ? 3u : (k.bvh1_index >= 0 ? 1u : 0u));
         // four kernels per executed iteration body (the last body may find the queue already empty) + wf_finalize
-        stats->kernel_launches = 4ull * w.h_flags[32 + CNT_BODIES] + 1ull;
+        stats->kernel_launches = (k.trace_pipeline ? 3ull : 4ull) * w.h_flags[32 + CNT_BODIES] + 1ull;
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
         stats->device_ms = ms;

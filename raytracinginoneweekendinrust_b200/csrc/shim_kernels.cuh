@@ -17,7 +17,8 @@
 //                that material: rebuild the HitRecord, emit, scatter, and append the continuing
 //                ray to the next ray queue (warp-ballot compaction, one atomic per warp)
 //                (wf_extend_solo / wf_extend_list / wf_extend_bvh1: the same walk with what a
-//                scene cannot need compiled out - fewer registers, more resident warps)
+//                scene cannot need compiled out - fewer registers, more resident warps;
+//                wf_trace_solo: shade + walk in one kernel, material queue to material queue)
 //   wf_tail      once no samples are left to start and at most 65536 paths are alive, one
 //                launch finishes them (extend + shade in a loop per thread) instead of ~35
 //                near-empty iterations; it also decides whether the loop goes on
@@ -32,9 +33,10 @@
 namespace shim {
 
 enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..6 */, CNT_CUR = 7, CNT_TICKET = 8, CNT_NEXT_CUR = 9, CNT_DONE = 10, CNT_ITER = 11,
-       CNT_BODIES = 12 /* iteration bodies executed */, CNT_GEN_BASE = 13 /* fused generation: queue slot of the first new sample */, CNT_U64_BASE = 14 /* u64 slots from here, as pairs */ };
+       CNT_BODIES = 12 /* iteration bodies executed */, CNT_GEN_BASE = 13 /* fused generation: queue slot of the first new sample */, CNT_U64_BASE = 14 /* u64 slots from here, as pairs */,
+       CNT_MQ1 = 32 /* ..36: second material-queue counter set (wf_trace pipeline) */, CNT_GEN_N = 37 /* new samples of this iteration */ };
 enum { C64_NEXT_SAMPLE = 0, C64_RAYS = 1, C64_NODES = 2, C64_PRIMS = 3, C64_HRPP_TP = 4, C64_HRPP_FP = 5, C64_HRPP_NONE = 6, C64_GEN_FIRST = 7, C64_COUNT = 8 };
-enum { CNT_WORDS = CNT_U64_BASE + 2 * C64_COUNT };
+enum { CNT_WORDS = 40 };
 
 // shared-memory image of the scene arrays wf_extend walks (byte offsets, all multiples of 16)
 struct SmemLayout {
@@ -66,6 +68,7 @@ struct WfParams {
     int has_media, count_nodes, use_hrpp;
     int bvh1_tri_threads;   // > 0: the one Bvh holds only triangles: wf_extend_bvh1<.., THREADS, PT_TRI>
     int list_threads; // > 0: the world has no Bvh: wf_extend_list with this many threads per block
+    int trace_pipeline;   // the iteration is wf_generate (counters only) + wf_trace (shade -> closest hit) + wf_tail_mq; no ray queues
     int fused_generate;   // wf_generate only publishes the counters; wf_extend_solo makes the camera rays itself
     int solo_only;    // wf_extend_solo: the one primitive type of the Bvh (PT_*), or -1 when mixed
     int solo;         // > 0: the world is exactly one plain Bvh: wf_extend_solo with this many threads per block
@@ -83,6 +86,10 @@ __constant__ WfParams g_p;
 __device__ __forceinline__ unsigned long long* cnt64(uint32_t* cnt, int slot) {
     return reinterpret_cast<unsigned long long*>(cnt + CNT_U64_BASE) + slot;
 }
+
+// wf_trace pipeline: two material-queue sets (set s: counters mq_counts(p, s), entries from mq_base(p, s, kind))
+__device__ __forceinline__ uint32_t* mq_counts(const WfParams& p, int set) { return p.cnt + (set ? CNT_MQ1 : CNT_MQ); }
+__device__ __forceinline__ size_t mq_base(const WfParams& p, int set, int kind) { return ((size_t)set * MAT_KINDS + (size_t)kind) * p.pool; }
 
 // position for this lane in a queue, one atomic per warp; all 32 lanes must call it
 __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred) {
@@ -148,7 +155,11 @@ __global__ void __launch_bounds__(256) wf_generate() {
     const WfParams& p = g_p;
     uint32_t* c = p.cnt;
     const int cur = (int)c[CNT_NEXT_CUR];
-    const uint32_t n_cur = c[cur];
+    uint32_t n_cur = c[cur];
+    if (p.trace_pipeline) {   // paths alive = entries of material-queue set `cur` waiting to be shaded
+        n_cur = 0;
+        for (int k = 0; k < MAT_KINDS; ++k) n_cur += mq_counts(p, cur)[k];
+    }
     const unsigned long long first = *cnt64(c, C64_NEXT_SAMPLE);
     const unsigned long long remaining = p.total_samples - first;
     const unsigned long long room = (unsigned long long)(p.pool - n_cur);
@@ -174,11 +185,16 @@ __global__ void __launch_bounds__(256) wf_generate() {
             *cnt64(c, C64_NEXT_SAMPLE) = first + n;
             c[CNT_GEN_BASE] = n_cur;               // fused generation: queue slots n_cur .. n_cur + n - 1 are samples first ..
             *cnt64(c, C64_GEN_FIRST) = first;
-            c[cur] = n_cur + n;
-            c[1 - cur] = 0;
+            if (p.trace_pipeline) {
+                c[CNT_GEN_N] = n;
+                for (int k = 0; k < MAT_KINDS; ++k) mq_counts(p, 1 - cur)[k] = 0;   // wf_trace fills the other set (and counts its rays)
+            } else {
+                c[cur] = n_cur + n;
+                c[1 - cur] = 0;
 #pragma unroll
-            for (int k = 0; k < MAT_KINDS; ++k) c[CNT_MQ + k] = 0;
-            *cnt64(c, C64_RAYS) += (unsigned long long)(n_cur + n);
+                for (int k = 0; k < MAT_KINDS; ++k) c[CNT_MQ + k] = 0;
+                *cnt64(c, C64_RAYS) += (unsigned long long)(n_cur + n);
+            }
             c[CNT_ITER] += (n_cur + n == 0) ? 0u : 1u;
             c[CNT_BODIES] += 1u;
             __threadfence();
@@ -714,6 +730,166 @@ __global__ void __launch_bounds__(128) wf_tail() {
         __threadfence();
         uint32_t ticket = atomicAdd(p.cnt + CNT_TICKET, 1u);
         if (ticket == gridDim.x - 1) { p.cnt[CNT_TICKET] = 0; p.cnt[nxt] = 0; loop_publish(p, true); __threadfence(); }
+    }
+}
+
+// ---------------------------------------------------------------------------- trace pipeline (one-Bvh worlds)
+// Nearly every shaded hit continues (absorption is rare), so compacting the scattered rays into a ray queue only to
+// read them back buys nothing.  wf_trace goes from material queue to material queue: an entry of set `cur` is shaded by
+// the code of its material, the scattered ray is walked through the tree right away and the new hit is appended to its
+// material's queue in the other set; new samples enter as camera rays made on the spot.  Per ray and bounce that is one
+// 64-byte read and one 64-byte write instead of 224 bytes through two queues, and two launches less per iteration.
+template <int KIND>
+__device__ __forceinline__ bool trace_shade_entry(const WfParams& p, int set, uint32_t j, f4& o, f4& d, f4& t) {
+    const size_t q = mq_base(p, set, KIND) + j;
+    const f4 eo = p.mq_o[q], ed = p.mq_d[q], et = p.mq_thr[q], hv = p.mq_hit[q];
+    Ray r; r.o = mk3(eo.x, eo.y, eo.z); r.d = mk3(ed.x, ed.y, ed.z); r.time = eo.w;
+    const uint32_t bs = (uint32_t)f2i(ed.w), pixel = (uint32_t)f2i(et.w);
+    Hit h; h.t = hv.x; h.obj = f2i(hv.y) & 0xffff; h.face = f2i(hv.y) >> 16; h.prim = (uint32_t)f2i(hv.z);
+    ShadeOut so;
+    so.cont = false; so.ray.o = mk3(0, 0, 0); so.ray.d = mk3(0, 0, 0); so.ray.time = 0; so.thr = mk3(0, 0, 0);
+    shade_one<KIND>(p, p.sv, r, h, f2i(hv.w), mk3(et.x, et.y, et.z), (int)(bs & 255u), pixel, bs >> 8, so);
+    if (!so.cont) return false;
+    o.x = so.ray.o.x; o.y = so.ray.o.y; o.z = so.ray.o.z; o.w = so.ray.time;
+    d.x = so.ray.d.x; d.y = so.ray.d.y; d.z = so.ray.d.z; d.w = i2f((int)(bs + 1u));
+    t.x = so.thr.x; t.y = so.thr.y; t.z = so.thr.z; t.w = i2f((int)pixel);
+    return true;
+}
+
+template <int THREADS, int ONLY>
+__global__ void __launch_bounds__(THREADS, 1) wf_trace_solo() {
+    const WfParams& p = g_p;
+    const int cur = (int)p.cnt[CNT_CUR];
+    // work items: the new samples, then the entries of the five queues of set `cur`, every segment padded to whole warps
+    uint32_t seg_n[MAT_KINDS + 1], seg_start[MAT_KINDS + 2];
+    seg_n[0] = p.cnt[CNT_GEN_N];
+#pragma unroll
+    for (int k = 0; k < MAT_KINDS; ++k) seg_n[k + 1] = mq_counts(p, cur)[k];
+    seg_start[0] = 0;
+#pragma unroll
+    for (int k = 0; k <= MAT_KINDS; ++k) seg_start[k + 1] = seg_start[k] + ((seg_n[k] + 31u) & ~31u);
+    const uint32_t total = seg_start[MAT_KINDS + 1];
+    if (blockIdx.x * blockDim.x >= total) return;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    const SceneView sv = stage_scene(p, smem, &bar);
+    const unsigned long long gen_first = *cnt64(p.cnt, C64_GEN_FIRST);
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t* out_cnt = mq_counts(p, 1 - cur);
+    uint32_t traced = 0;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
+        f4 o, d, t;
+        bool have = false;
+        // which segment (the same for the whole warp)
+        if (slot < seg_start[1]) { const uint32_t j = slot; if (j < seg_n[0]) { camera_ray_record(p, gen_first + j, o, d, t); have = true; } }
+        else if (slot < seg_start[2]) { const uint32_t j = slot - seg_start[1]; if (j < seg_n[1]) have = trace_shade_entry<MAT_LAMBERTIAN>(p, cur, j, o, d, t); }
+        else if (slot < seg_start[3]) { const uint32_t j = slot - seg_start[2]; if (j < seg_n[2]) have = trace_shade_entry<MAT_METAL>(p, cur, j, o, d, t); }
+        else if (slot < seg_start[4]) { const uint32_t j = slot - seg_start[3]; if (j < seg_n[3]) have = trace_shade_entry<MAT_DIELECTRIC>(p, cur, j, o, d, t); }
+        else if (slot < seg_start[5]) { const uint32_t j = slot - seg_start[4]; if (j < seg_n[4]) have = trace_shade_entry<MAT_DIFFUSE_LIGHT>(p, cur, j, o, d, t); }
+        else { const uint32_t j = slot - seg_start[5]; if (j < seg_n[5]) have = trace_shade_entry<MAT_ISOTROPIC>(p, cur, j, o, d, t); }
+        int kind = 7;
+        f4 hv;
+        if (have) {
+            ++traced;
+            Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
+            if (!ray_has_nan(r)) {   // see extend_rays
+                TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
+                const Hit h = closest_hit_solo<false, ONLY>(sv, r, 0.001f, SHIM_INF, &tc);
+                if (h.obj < 0) {  // ray.rs:60
+                    if (p.bg[0] != 0.0f || p.bg[1] != 0.0f || p.bg[2] != 0.0f) {
+                        float* a = p.accum + 3 * (size_t)(uint32_t)f2i(t.w);
+                        atomicAdd(a + 0, t.x * p.bg[0]);
+                        atomicAdd(a + 1, t.y * p.bg[1]);
+                        atomicAdd(a + 2, t.z * p.bg[2]);
+                    }
+                } else {
+                    const int mw = ONLY == PT_SPHERE ? sv.sph_mat[prim_index(h.prim)] : hit_material_word(sv, h);
+                    kind = mat_word_kind(mw);
+                    hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat_word_index(mw));
+                }
+            }
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, kind);
+        if (kind < MAT_KINDS) {
+            const int leader = __ffs(grp) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(out_cnt + kind, (uint32_t)__popc(grp));
+            base = __shfl_sync(grp, base, leader);
+            const size_t pos = mq_base(p, 1 - cur, kind) + base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+            p.mq_o[pos] = o; p.mq_d[pos] = d; p.mq_thr[pos] = t; p.mq_hit[pos] = hv;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);
+    if (lane == 0 && traced) atomicAdd(cnt64(p.cnt, C64_RAYS), (unsigned long long)traced);
+}
+
+// wf_tail for the trace pipeline: the survivors are material-queue entries (hits waiting to be shaded)
+template <int ONLY>
+__global__ void __launch_bounds__(128) wf_tail_mq() {
+    const WfParams& p = g_p;
+    const int nxt = 1 - (int)p.cnt[CNT_CUR];
+    uint32_t seg_n[MAT_KINDS], n = 0;
+#pragma unroll
+    for (int k = 0; k < MAT_KINDS; ++k) { seg_n[k] = mq_counts(p, nxt)[k]; n += seg_n[k]; }
+    const bool all_started = *cnt64(p.cnt, C64_NEXT_SAMPLE) >= p.total_samples;
+    if (n == 0 || n > p.tail_threshold || !all_started) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) loop_publish(p, n == 0 && all_started);
+        return;
+    }
+    uint32_t traced = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int kind = 0;
+        uint32_t j = i;
+        while (j >= seg_n[kind]) { j -= seg_n[kind]; ++kind; }
+        const size_t q = mq_base(p, nxt, kind) + j;
+        const f4 eo = p.mq_o[q], ed = p.mq_d[q], et = p.mq_thr[q], hv = p.mq_hit[q];
+        Ray r; r.o = mk3(eo.x, eo.y, eo.z); r.d = mk3(ed.x, ed.y, ed.z); r.time = eo.w;
+        const uint32_t sample = (uint32_t)f2i(ed.w) >> 8, pixel = (uint32_t)f2i(et.w);
+        int bounce = f2i(ed.w) & 255;
+        f3 thr = mk3(et.x, et.y, et.z);
+        Hit h; h.t = hv.x; h.obj = f2i(hv.y) & 0xffff; h.face = f2i(hv.y) >> 16; h.prim = (uint32_t)f2i(hv.z);
+        int mat = f2i(hv.w);
+        for (;;) {
+            ShadeOut so;
+            so.cont = false;
+            switch (kind) {
+            case MAT_LAMBERTIAN: shade_one<MAT_LAMBERTIAN>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            case MAT_METAL: shade_one<MAT_METAL>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            case MAT_DIELECTRIC: shade_one<MAT_DIELECTRIC>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            case MAT_DIFFUSE_LIGHT: shade_one<MAT_DIFFUSE_LIGHT>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            default: shade_one<MAT_ISOTROPIC>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
+            }
+            if (!so.cont) break;
+            r = so.ray; thr = so.thr; ++bounce;
+            ++traced;
+            if (ray_has_nan(r)) break;
+            TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
+            h = closest_hit_solo<false, ONLY>(p.sv, r, 0.001f, SHIM_INF, &tc);
+            if (h.obj < 0) {
+                float* a = p.accum + 3 * (size_t)pixel;
+                atomicAdd(a + 0, thr.x * p.bg[0]);
+                atomicAdd(a + 1, thr.y * p.bg[1]);
+                atomicAdd(a + 2, thr.z * p.bg[2]);
+                break;
+            }
+            const int mw = hit_material_word(p.sv, h);
+            mat = mat_word_index(mw);
+            kind = mat_word_kind(mw);
+        }
+    }
+    unsigned long long extra = traced;
+    for (int off = 16; off > 0; off >>= 1) extra += __shfl_down_sync(0xffffffffu, extra, off);
+    if ((threadIdx.x & 31) == 0 && extra) atomicAdd(cnt64(p.cnt, C64_RAYS), extra);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t ticket = atomicAdd(p.cnt + CNT_TICKET, 1u);
+        if (ticket == gridDim.x - 1) {
+            p.cnt[CNT_TICKET] = 0;
+            for (int k = 0; k < MAT_KINDS; ++k) mq_counts(p, nxt)[k] = 0;
+            loop_publish(p, true);
+            __threadfence();
+        }
     }
 }
 

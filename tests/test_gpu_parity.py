@@ -129,19 +129,24 @@ def _render_with_env(g, cam, params, env, out=None):
 
 
 def test_kernel_variants_agree():
-    """The device-side WHILE-node loop vs the host-driven loop, camera rays made inside wf_extend_solo vs written by
-    wf_generate, wf_extend_solo vs the generic wf_extend and wf_tail vs plain iterations trace the same rays and give the same image (radiance sums differ only in atomicAdd order)."""
+    """The wf_trace pipeline vs the wavefront pipeline, the device-side WHILE-node loop vs the host-driven loop, camera
+    rays made inside wf_extend_solo vs written by wf_generate, wf_extend_solo vs the generic wf_extend and the tail
+    kernels vs plain iterations trace the same rays and give the same image (radiance sums differ only in atomicAdd order)."""
     g, o, info = build_pair("random-spheres")
     cam = CAMERAS["random-spheres"]
     p = api.make_params(192, 128, 6, 50, background=info.background, seed=5)
     ref, st = g.render(cam, p)
-    assert st.extend_variant == 2                  # one plain Bvh of spheres -> wf_extend_solo
-    for env in ({"SHIM_NO_GRAPH": "1"}, {"SHIM_NO_FUSE": "1"}, {"SHIM_SOLO": "0"}, {"SHIM_SOLO": "768", "SHIM_SOLO_ANY": "1"}, {"SHIM_TAIL": "0"},
+    assert st.extend_variant == 4                  # one plain Bvh of spheres -> the wf_trace pipeline
+    for env in ({"SHIM_NO_GRAPH": "1"}, {"SHIM_TRACE_T": "640", "SHIM_SOLO_ANY": "1"}, {"SHIM_TAIL": "0"},
+                {"SHIM_NO_TRACE": "1"}, {"SHIM_NO_TRACE": "1", "SHIM_NO_FUSE": "1"}, {"SHIM_SOLO": "0"},
+                {"SHIM_NO_TRACE": "1", "SHIM_SOLO": "768", "SHIM_SOLO_ANY": "1"}, {"SHIM_NO_TRACE": "1", "SHIM_TAIL": "0"},
                 {"SHIM_SOLO": "0", "SHIM_NO_GRAPH": "1", "SHIM_TAIL": "0"}):
         img, st2 = _render_with_env(g, cam, p, env)
         assert st2.rays == st.rays, env
         if env.get("SHIM_SOLO") == "0":
             assert st2.extend_variant == 0
+        elif "SHIM_NO_TRACE" in env:
+            assert st2.extend_variant == 2         # wavefront pipeline with wf_extend_solo
         np.testing.assert_allclose(img, ref, rtol=2e-5, atol=2e-6, err_msg=str(env))
 
 
