@@ -513,7 +513,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         if (const char* e = getenv("SHIM_SOLO")) k.solo = atoi(e);
         k.fused_generate = (k.solo && !getenv("SHIM_NO_FUSE")) ? 1 : 0;
         if (k.solo && !getenv("SHIM_NO_TRACE")) {
-            k.trace_pipeline = 896;   // Book-1: 3.00 ms wavefront, 3.28 / 3.00 / 2.92 / 2.91 ms at 512 / 640 / 768 / 896 threads
+            k.trace_pipeline = spheres_only ? 896 : 768;   // Book-1: 3.00 ms wavefront, 3.28 / 3.00 / 2.92 / 2.91 ms at 512 / 640 / 768 / 896 threads
             if (const char* e = getenv("SHIM_TRACE_T")) k.trace_pipeline = atoi(e);
             if (k.trace_pipeline) k.fused_generate = 1;   // wf_generate only publishes counters in this pipeline
         }
