@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(128) wf_tail() {
 // material's queue in the other set; new samples enter as camera rays made on the spot.  Per ray and bounce that is one
 // 64-byte read and one 64-byte write instead of 224 bytes through two queues, and two launches less per iteration.
 template <int KIND>
-__device__ __forceinline__ bool trace_shade_entry(const WfParams& p, int set, uint32_t j, f4& o, f4& d, f4& t) {
+__device__ __noinline__ bool trace_shade_entry(const WfParams& p, int set, uint32_t j, f4& o, f4& d, f4& t) {
     const size_t q = mq_base(p, set, KIND) + j;
     const f4 eo = p.mq_o[q], ed = p.mq_d[q], et = p.mq_thr[q], hv = p.mq_hit[q];
     Ray r; r.o = mk3(eo.x, eo.y, eo.z); r.d = mk3(ed.x, ed.y, ed.z); r.time = eo.w;
