@@ -268,7 +268,7 @@ static int wf_prepare(shim_scene* s, const shim_render_params& p) {
         w.grid_tail = sms * 4;
 #define SHIM_TRACE_ATTR(T) CU(cudaFuncSetAttribute(wf_trace_solo<T, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
                            CU(cudaFuncSetAttribute(wf_trace_solo<T, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
-        SHIM_TRACE_ATTR(512); SHIM_TRACE_ATTR(640); SHIM_TRACE_ATTR(768); SHIM_TRACE_ATTR(896);
+        SHIM_TRACE_ATTR(512); SHIM_TRACE_ATTR(640); SHIM_TRACE_ATTR(768); SHIM_TRACE_ATTR(896); SHIM_TRACE_ATTR(1024);
 #undef SHIM_TRACE_ATTR
 #define SHIM_LIST_ATTR(T) CU(cudaFuncSetAttribute(wf_extend_list<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
                           CU(cudaFuncSetAttribute(wf_extend_list<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
@@ -381,6 +381,7 @@ static void launch_trace(const Wavefront& w, const WfParams& k, cudaStream_t st)
     case 512: SHIM_TRACE_T(512); break;
     case 640: SHIM_TRACE_T(640); break;
     case 768: SHIM_TRACE_T(768); break;
+    case 1024: SHIM_TRACE_T(1024); break;
     default: SHIM_TRACE_T(896); break;
     }
 #undef SHIM_TRACE_T
