@@ -160,3 +160,21 @@ def test_page_locked_framebuffer_path_matches_staged_path():
     assert st2.rays == st.rays
     np.testing.assert_allclose(np.array(direct), staged, rtol=2e-5, atol=2e-6)
     fb.close()
+
+
+def test_small_pool_in_the_trace_pipeline():
+    """Book-1 (wf_trace pipeline) with a pool far smaller than the sample count: many regeneration rounds, the same
+    image and ray count as with everything in flight at once, also for a sample-range shard."""
+    g, o, info = build_pair("random-spheres")
+    cam = CAMERAS["random-spheres"]
+    W, H, spp = 96, 64, 8
+    big, st = g.render(cam, api.make_params(W, H, spp, 50, background=info.background, seed=3))
+    small, st2 = g.render(cam, api.make_params(W, H, spp, 50, background=info.background, seed=3, pool_paths=2048))
+    assert st.extend_variant == 4 and st2.extend_variant == 4
+    assert st2.iterations > 30 and st2.rays == st.rays
+    np.testing.assert_allclose(small, big, rtol=2e-5, atol=2e-6)
+    raw = capi.RENDER_RAW_SUM
+    a, _ = g.render(cam, api.make_params(W, H, spp, 50, background=info.background, seed=3, sample_begin=0, sample_count=3, flags=raw))
+    b, _ = g.render(cam, api.make_params(W, H, spp, 50, background=info.background, seed=3, sample_begin=3, sample_count=5, flags=raw,
+                                         pool_paths=4096))
+    np.testing.assert_allclose((a + b) / spp, big, rtol=2e-5, atol=2e-6)
