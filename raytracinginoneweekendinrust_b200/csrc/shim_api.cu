@@ -390,8 +390,7 @@ static void launch_tail_mq(const Wavefront& w, const WfParams& k, cudaStream_t s
     if (k.solo_only == PT_SPHERE) wf_tail_mq<PT_SPHERE><<<w.grid_tail, 128, 0, st>>>(); else wf_tail_mq<-1><<<w.grid_tail, 128, 0, st>>>();
 }
 static void launch_iteration(const Wavefront& w, const WfParams& k, bool use_smem, cudaStream_t st) {
-    if (k.trace_pipeline) {   // counters, shade -> closest hit, endgame / loop condition
-        wf_generate<<<w.grid_generate, 256, 0, st>>>();
+    if (k.trace_pipeline) {   // shade -> closest hit, then endgame / loop condition / counters of the next iteration
         launch_trace(w, k, st);
         launch_tail_mq(w, k, st);
         return;
@@ -561,6 +560,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     if (use_graph) { int grc = loop_graph(w, k, use_smem, &lg); if (grc < 0) return grc; }
     k.loop_handle = lg.handle;
     CU(cudaMemcpyToSymbolAsync(g_p, &k, sizeof k, 0, cudaMemcpyHostToDevice, st));
+    if (run && k.trace_pipeline) wf_trace_first<<<1, 32, 0, st>>>();   // counters of iteration 0 (later ones: wf_tail_mq)
     if (use_graph) {
         CU(cudaGraphLaunch(lg.exec, st));
     } else if (run) {
@@ -572,7 +572,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
             for (int it = 0; it < SHIM_CHUNK; ++it) {
                 const bool rec = profile && prof_used + 4 <= prof_cap;
                 if (rec) CU(cudaEventRecord(w.prof[prof_used], st));
-                wf_generate<<<w.grid_generate, 256, 0, st>>>();
+                if (!k.trace_pipeline) wf_generate<<<w.grid_generate, 256, 0, st>>>();
                 if (rec) CU(cudaEventRecord(w.prof[prof_used + 1], st));
                 if (k.trace_pipeline) launch_trace(w, k, st);
                 else launch_extend(k, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
@@ -611,7 +611,8 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         stats->iterations = w.h_flags[32 + CNT_ITER];
         stats->extend_variant = k.trace_pipeline ? 4u : k.solo ? 2u : (k.list_threads ? 3u : (k.bvh1_index >= 0 ? 1u : 0u));
         // four kernels per executed iteration body (the last body may find the queue already empty) + wf_finalize
-        stats->kernel_launches = (k.trace_pipeline ? 3ull : 4ull) * w.h_flags[32 + CNT_BODIES] + 1ull;
+        // trace pipeline: wf_trace_first + two kernels per iteration body + wf_finalize; wavefront: four per body + wf_finalize
+        stats->kernel_launches = k.trace_pipeline ? 2ull * w.h_flags[32 + CNT_BODIES] + 2ull : 4ull * w.h_flags[32 + CNT_BODIES] + 1ull;
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
         stats->device_ms = ms;

@@ -68,7 +68,7 @@ struct WfParams {
     int has_media, count_nodes, use_hrpp;
     int bvh1_tri_threads;   // > 0: the one Bvh holds only triangles: wf_extend_bvh1<.., THREADS, PT_TRI>
     int list_threads; // > 0: the world has no Bvh: wf_extend_list with this many threads per block
-    int trace_pipeline;   // the iteration is wf_generate (counters only) + wf_trace (shade -> closest hit) + wf_tail_mq; no ray queues
+    int trace_pipeline;   // the iteration is wf_trace (shade -> closest hit) + wf_tail_mq (endgame, loop condition, next counters); no ray queues
     int fused_generate;   // wf_generate only publishes the counters; wf_extend_solo makes the camera rays itself
     int solo_only;    // wf_extend_solo: the one primitive type of the Bvh (PT_*), or -1 when mixed
     int solo;         // > 0: the world is exactly one plain Bvh: wf_extend_solo with this many threads per block
@@ -155,11 +155,7 @@ __global__ void __launch_bounds__(256) wf_generate() {
     const WfParams& p = g_p;
     uint32_t* c = p.cnt;
     const int cur = (int)c[CNT_NEXT_CUR];
-    uint32_t n_cur = c[cur];
-    if (p.trace_pipeline) {   // paths alive = entries of material-queue set `cur` waiting to be shaded
-        n_cur = 0;
-        for (int k = 0; k < MAT_KINDS; ++k) n_cur += mq_counts(p, cur)[k];
-    }
+    const uint32_t n_cur = c[cur];
     const unsigned long long first = *cnt64(c, C64_NEXT_SAMPLE);
     const unsigned long long remaining = p.total_samples - first;
     const unsigned long long room = (unsigned long long)(p.pool - n_cur);
@@ -185,16 +181,11 @@ __global__ void __launch_bounds__(256) wf_generate() {
             *cnt64(c, C64_NEXT_SAMPLE) = first + n;
             c[CNT_GEN_BASE] = n_cur;               // fused generation: queue slots n_cur .. n_cur + n - 1 are samples first ..
             *cnt64(c, C64_GEN_FIRST) = first;
-            if (p.trace_pipeline) {
-                c[CNT_GEN_N] = n;
-                for (int k = 0; k < MAT_KINDS; ++k) mq_counts(p, 1 - cur)[k] = 0;   // wf_trace fills the other set (and counts its rays)
-            } else {
-                c[cur] = n_cur + n;
-                c[1 - cur] = 0;
+            c[cur] = n_cur + n;
+            c[1 - cur] = 0;
 #pragma unroll
-                for (int k = 0; k < MAT_KINDS; ++k) c[CNT_MQ + k] = 0;
-                *cnt64(c, C64_RAYS) += (unsigned long long)(n_cur + n);
-            }
+            for (int k = 0; k < MAT_KINDS; ++k) c[CNT_MQ + k] = 0;
+            *cnt64(c, C64_RAYS) += (unsigned long long)(n_cur + n);
             c[CNT_ITER] += (n_cur + n == 0) ? 0u : 1u;
             c[CNT_BODIES] += 1u;
             __threadfence();
@@ -668,6 +659,34 @@ __device__ __forceinline__ void loop_publish(const WfParams& p, bool done) {
     p.cnt[CNT_DONE] = done ? 1u : 0u;
     if (p.loop_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)p.loop_handle, done ? 0u : 1u);
 }
+// Trace pipeline: what wf_generate's last block publishes for the next iteration (it writes no rays there), done by
+// the one thread that ends the previous iteration in wf_tail_mq - the iteration is then two launches, not three.
+__device__ __forceinline__ void trace_prepare_iteration(const WfParams& p) {
+    uint32_t* c = p.cnt;
+    const int cur = (int)c[CNT_NEXT_CUR];
+    uint32_t n_cur = 0;
+    for (int k = 0; k < MAT_KINDS; ++k) n_cur += mq_counts(p, cur)[k];
+    const unsigned long long first = *cnt64(c, C64_NEXT_SAMPLE);
+    const unsigned long long remaining = p.total_samples - first;
+    const unsigned long long room = (unsigned long long)(p.pool - n_cur);
+    const uint32_t n = (uint32_t)(remaining < room ? remaining : room);
+    c[CNT_CUR] = (uint32_t)cur;
+    c[CNT_NEXT_CUR] = (uint32_t)(1 - cur);
+    *cnt64(c, C64_NEXT_SAMPLE) = first + n;
+    *cnt64(c, C64_GEN_FIRST) = first;
+    c[CNT_GEN_N] = n;
+    for (int k = 0; k < MAT_KINDS; ++k) mq_counts(p, 1 - cur)[k] = 0;   // wf_trace fills the other set
+    c[CNT_ITER] += (n_cur + n == 0) ? 0u : 1u;
+    c[CNT_BODIES] += 1u;
+}
+// after the last iteration: leave nothing for a further wf_trace launch to pick up (the host-driven loop enqueues a few)
+__device__ __forceinline__ void trace_finish(const WfParams& p) {
+    for (int k = 0; k < MAT_KINDS; ++k) { mq_counts(p, 0)[k] = 0; mq_counts(p, 1)[k] = 0; }
+    p.cnt[CNT_GEN_N] = 0;
+}
+__global__ void wf_trace_first() {   // before the loop: the counters of iteration 0
+    if (blockIdx.x == 0 && threadIdx.x == 0) { trace_prepare_iteration(g_p); __threadfence(); }
+}
 template <bool HRPP, bool SOLO = false, int ONLY = -1>
 __global__ void __launch_bounds__(128) wf_tail() {
     const WfParams& p = g_p;
@@ -833,7 +852,17 @@ __global__ void __launch_bounds__(128) wf_tail_mq() {
     for (int k = 0; k < MAT_KINDS; ++k) { seg_n[k] = mq_counts(p, nxt)[k]; n += seg_n[k]; }
     const bool all_started = *cnt64(p.cnt, C64_NEXT_SAMPLE) >= p.total_samples;
     if (n == 0 || n > p.tail_threshold || !all_started) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) loop_publish(p, n == 0 && all_started);
+        // the counters may only change once every block has read them: the last block to get here ends the iteration
+        if (threadIdx.x == 0) {
+            const uint32_t ticket = atomicAdd(p.cnt + CNT_TICKET, 1u);
+            if (ticket == gridDim.x - 1) {
+                p.cnt[CNT_TICKET] = 0;
+                const bool done = n == 0 && all_started;
+                loop_publish(p, done);
+                if (done) trace_finish(p); else trace_prepare_iteration(p);
+                __threadfence();
+            }
+        }
         return;
     }
     uint32_t traced = 0;
@@ -886,7 +915,7 @@ __global__ void __launch_bounds__(128) wf_tail_mq() {
         uint32_t ticket = atomicAdd(p.cnt + CNT_TICKET, 1u);
         if (ticket == gridDim.x - 1) {
             p.cnt[CNT_TICKET] = 0;
-            for (int k = 0; k < MAT_KINDS; ++k) mq_counts(p, nxt)[k] = 0;
+            trace_finish(p);
             loop_publish(p, true);
             __threadfence();
         }
