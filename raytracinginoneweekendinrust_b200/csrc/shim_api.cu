@@ -367,7 +367,7 @@ static void launch_extend(const WfParams& k, int grid, uint32_t smem, cudaStream
 
 // one wavefront iteration on `st` (the parameters are already in constant memory, the queue index in the counters)
 static void launch_tail(const Wavefront& w, const WfParams& k, cudaStream_t st) {
-    if (k.solo && !getenv("SHIM_NO_SOLO_TAIL")) {
+    if (k.solo) {
         if (k.solo_only == PT_SPHERE) wf_tail<false, true, PT_SPHERE><<<w.grid_tail, 128, 0, st>>>(); else wf_tail<false, true, -1><<<w.grid_tail, 128, 0, st>>>();
         return;
     }
