@@ -84,3 +84,32 @@ def test_unsupported_nesting_is_reported_at_commit():
             s.commit()
         assert e.value.code in (-2, -3)   # -3 only if flatten passed, which it must not
         assert e.value.code == -2, e.value.message
+
+
+def test_host_framebuffer_allocator_needs_a_device_too():
+    """shim_host_alloc hands out page-locked memory: without a CUDA device it fails with a message instead of
+    falling back to malloc (a pageable buffer works with shim_render anyway)."""
+    import torch
+    if torch.cuda.is_available():
+        fb = api.HostFramebuffer(4, 8)
+        assert fb.array.shape == (4, 8, 3) and fb.array.dtype == np.float32
+        fb.array[:] = 1.0
+        fb.close()
+        fb.close()          # idempotent
+    else:
+        with pytest.raises(capi.ShimError) as e:
+            api.HostFramebuffer(4, 8)
+        assert "shim_host_alloc" in str(e.value)
+
+
+def test_device_tree_is_built_with_the_bvh():
+    """Bvh::new's stand-in builds the tree the kernels walk as well, so commit only lays it out: shim_bvh_info reports
+    the recorded bvh.rs tree, and a scene whose Bvh holds a member the device cannot walk fails at commit, not before."""
+    s = api.Scene()
+    m = s.material_lambertian(s.texture_solid(0.5, 0.5, 0.5))
+    lst = s.list_create()
+    for i in range(9):
+        s.list_add(lst, s.sphere((float(i), 0.0, 0.0), 0.4, m))
+    b = s.bvh(lst, 0.0, 1.0, seed=3)
+    n_nodes, root, height = s.bvh_info(b)
+    assert n_nodes >= 8 and 0 <= root < n_nodes and height >= 4
