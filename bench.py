@@ -41,7 +41,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    """SM clock + throttle reasons sampled during the timed region: NVML in a thread (every 2 ms; a Book-1 timed
+    region lasts ~60 ms), nvidia-smi -lms as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -51,8 +52,34 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []      # (sm MHz, max MHz, reasons bitmask)
+        self._stop = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].strip().isdigit() else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx,
+                                             pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                    except Exception:
+                        break
+                    time.sleep(0.002)
+
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -65,7 +92,23 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def _stop_nvml(self) -> dict:
+        self._stop.set()
+        self.t.join(timeout=1)
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, b in bits.items() if any(s[2] & b for s in self.samples))
+        sm = [s[0] for s in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.samples[0][1]) if sm else None,
+                "reasons": reasons, "samples": len(sm), "source": "nvml"}
+
     def stop(self) -> dict:
+        if self.nvml is not None:
+            try:
+                return self._stop_nvml()
+            except Exception as e:   # fall through to whatever nvidia-smi gathered (nothing, if it was not started)
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml: {e}"]}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
