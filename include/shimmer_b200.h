@@ -123,7 +123,8 @@ typedef struct shim_render_params {
     float background[3];
     uint64_t seed;                 /* Philox key */
     int32_t sample_begin;          /* first absolute sample index rendered by this call */
-    int32_t sample_count;          /* samples per pixel rendered by this call; 0 = samples_per_pixel */
+    int32_t sample_count;          /* samples per pixel rendered by this call; 0 = samples_per_pixel, -1 = none
+                                      (a shard that owns no samples: the framebuffer comes back zero) */
     int32_t tile_rank, tile_world; /* tile sharding: this call renders tiles with index % world == rank (world 0/1 = all) */
     int32_t flags;                 /* SHIM_RENDER_* */
     int32_t pool_paths;            /* wavefront pool size; 0 = default */
@@ -140,6 +141,10 @@ typedef struct shim_stats {
     double extend_ms, shade_ms, generate_ms; /* event sums per kernel class (extend only, with SHIM_RENDER_PROFILE) */
     uint64_t extend_launches;      /* wf_extend launches that had rays, covered by extend_ms */
     uint64_t extend_variant;       /* which closest-hit kernel ran: 0 wf_extend, 1 wf_extend_bvh1, 2 wf_extend_solo, 3 wf_extend_list, 4 wf_trace_solo */
+    uint64_t pool_paths;           /* paths in flight this render was given (min(samples, 2^24) unless pool_paths says otherwise) */
+    uint64_t pool_bytes;           /* device memory of the wavefront pool(s) after this render (queues, counters, framebuffers) */
+    uint64_t devices;              /* devices that rendered (1 except for shim_render_multi) */
+    double wall_ms;                /* host wall time of the whole call incl. the framebuffer copy (shim_render, shim_render_multi) */
 } shim_stats;
 
 /* host framebuffer: width*height*3 floats, linear radiance, row-major, y = 0 is the bottom row
@@ -153,6 +158,20 @@ void shim_host_free(float* p);
 /* same, into a device buffer of the current device on `cuda_stream` (0 = default stream) */
 int shim_render_device(shim_scene* s, const shim_camera* cam, const shim_render_params* p, float* d_out_rgb,
                        shim_stats* stats, void* cuda_stream);
+
+/* One image on several devices of this process — the tile fan-out of Renderer::render (renderer.rs:63-95) across
+ * GPUs instead of threads.  The scene is replicated on first use; device i renders its shard on its own host thread
+ * and stream with private accumulation (SHIM_SHARD_SAMPLES: a contiguous range of absolute sample indices;
+ * SHIM_SHARD_TILES: the tiles with index % n_devices == i); the sums are combined once at the end on devices[0]
+ * (peer copies + add) and the mean lands in out_rgb (host).  devices = NULL: ordinals 0 .. n_devices-1;
+ * n_devices <= 0: every device.  stats: rays/samples summed, device_ms = the slowest device's loop. */
+enum { SHIM_SHARD_SAMPLES = 0, SHIM_SHARD_TILES = 1 };
+int shim_render_multi(shim_scene* s, const shim_camera* cam, const shim_render_params* p, int n_devices, const int* devices,
+                      int mode, float* out_rgb, shim_stats* stats);
+/* Releases every device's wavefront pool (queues, graphs, events, staging buffers).  Scenes stay valid; the next
+ * render allocates again.  No render may be in flight.  shim_pool_bytes: what a device's pool holds right now. */
+int shim_shutdown(void);
+uint64_t shim_pool_bytes(int device);
 
 /* ---- gate 1: closest hit for a batch of rays (Hittable::hit on the world, hittable.rs:100-118)
  * rays: n x 7 floats (origin, direction, time).  prim_id: hittable id or -1; t: hit parameter

@@ -60,6 +60,24 @@ class Scene(capi.SceneHandle):
             raise ShimError(rc, self.lib.shim_last_error().decode())
         return out, st
 
+    def render_multi(self, camera: Camera, params: RenderParams, n_devices: int = 0, devices=None, mode: str = "samples",
+                     out: np.ndarray | None = None):
+        """One image sharded over several devices of this process (``shim_render_multi``): sample ranges or tiles,
+        per-device accumulation, one combine at the end.  Returns the host framebuffer and the summed Stats."""
+        if out is None:
+            out = np.empty((params.height, params.width, 3), np.float32)
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.shape == (params.height, params.width, 3)
+        dev = None
+        if devices is not None:
+            dev = (C.c_int * len(devices))(*devices)
+            n_devices = len(devices)
+        st = Stats()
+        rc = self.lib.shim_render_multi(self.ptr, C.byref(camera), C.byref(params), n_devices, dev,
+                                        {"samples": capi.SHARD_SAMPLES, "tiles": capi.SHARD_TILES}[mode], out.ctypes.data, C.byref(st))
+        if rc < 0:
+            raise ShimError(rc, self.lib.shim_last_error().decode())
+        return out, st
+
     def render_device(self, camera: Camera, params: RenderParams, d_out_ptr: int, stream: int = 0) -> Stats:
         """Render into a device buffer (e.g. ``torch.Tensor.data_ptr()``) on ``stream``."""
         st = Stats()
@@ -93,6 +111,15 @@ class HostFramebuffer:
             self.close()
         except Exception:
             pass
+
+
+def shutdown() -> None:
+    """Release every device's wavefront pool (``shim_shutdown``); scenes stay valid."""
+    capi.load_library().shim_shutdown()
+
+
+def pool_bytes(device: int = 0) -> int:
+    return int(capi.load_library().shim_pool_bytes(device))
 
 
 def make_params(width, height, spp, max_depth=50, tile_width=8, tile_height=8, background=(0.0, 0.0, 0.0), seed=0,

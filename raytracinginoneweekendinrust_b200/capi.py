@@ -58,6 +58,8 @@ RENDER_RAW_SUM = 1
 RENDER_PREDICTORS = 2
 RENDER_COUNT_NODES = 4
 RENDER_PROFILE = 8
+SHARD_SAMPLES = 0
+SHARD_TILES = 1
 
 
 class RenderParams(C.Structure):
@@ -75,7 +77,8 @@ class Stats(C.Structure):
         ("hrpp_true_positive", C.c_uint64), ("hrpp_false_positive", C.c_uint64), ("hrpp_no_prediction", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("iterations", C.c_uint64), ("device_ms", C.c_double),
         ("extend_ms", C.c_double), ("shade_ms", C.c_double), ("generate_ms", C.c_double), ("extend_launches", C.c_uint64),
-        ("extend_variant", C.c_uint64),
+        ("extend_variant", C.c_uint64), ("pool_paths", C.c_uint64), ("pool_bytes", C.c_uint64), ("devices", C.c_uint64),
+        ("wall_ms", C.c_double),
     ]
 
     EXTEND_KERNELS = {0: "wf_extend", 1: "wf_extend_bvh1", 2: "wf_extend_solo", 3: "wf_extend_list", 4: "wf_trace_solo"}
@@ -159,6 +162,12 @@ def load_library() -> C.CDLL:
     lib.shim_render.argtypes = [_P, C.POINTER(Camera), C.POINTER(RenderParams), _P, C.POINTER(Stats)]
     lib.shim_render_device.restype = _I
     lib.shim_render_device.argtypes = [_P, C.POINTER(Camera), C.POINTER(RenderParams), _P, C.POINTER(Stats), _P]
+    lib.shim_render_multi.restype = _I
+    lib.shim_render_multi.argtypes = [_P, C.POINTER(Camera), C.POINTER(RenderParams), _I, _P, _I, _P, C.POINTER(Stats)]
+    lib.shim_shutdown.restype = _I
+    lib.shim_shutdown.argtypes = []
+    lib.shim_pool_bytes.restype = C.c_uint64
+    lib.shim_pool_bytes.argtypes = [_I]
     lib.shim_trace_closest.restype = _I
     lib.shim_trace_closest.argtypes = [_P, _P, C.c_int64, _F, _F, C.c_uint64, _P, _P, _P]
     lib.shim_trace_closest_device.restype = _I

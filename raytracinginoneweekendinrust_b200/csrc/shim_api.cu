@@ -1,5 +1,5 @@
-// shim_api.cu — the C ABI (include/shimmer_b200.h): scene recording, commit/upload, the
-// wavefront driver and the gate-1 batch query.  No CPU fallback: every device entry point
+// shim_api.cu — the C ABI (include/shimmer_b200.h): commit/upload, the wavefront driver, the
+// multi-device render and the gate-1 batch query.  No CPU fallback: every device entry point
 // fails with SHIM_ERR_CUDA when no CUDA device is usable.
 #include <cuda_runtime.h>
 #include <chrono>
@@ -9,9 +9,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "shim_internal.h"
@@ -44,95 +46,176 @@ struct DevBuf {
     cudaError_t alloc(size_t count) {
         release();
         n = count;
-        return cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+        cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; n = 0; }
+        return e;
     }
+    cudaError_t reserve(size_t count) { return count <= n && p ? cudaSuccess : alloc(count); }   // grow only
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return p ? (n ? n : 1) * sizeof(T) : 0; }
 };
 
-// A committed scene is ONE device allocation filled by ONE host-to-device copy: the arrays are packed
-// back to back (256-byte aligned) in a host staging blob first.
+// restores the calling thread's current device
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t enter(int device) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev != device) { e = cudaSetDevice(device); changed = e == cudaSuccess; }
+        return e;
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+// Host image of a committed scene: the arrays packed back to back (256-byte aligned), uploaded with ONE copy per
+// device.  It is kept after commit so that shim_render_multi can replicate the scene on further devices.
+struct SceneBlob {
+    std::vector<unsigned char> bytes;
+    size_t o_nodes = 0, o_sph = 0, o_sph_s = 0, o_sph_mat = 0, o_msph = 0, o_rect = 0, o_tri = 0, o_cube = 0, o_obj = 0, o_mat = 0, o_tex = 0,
+           o_img = 0, o_perlin = 0;
+    size_t o_handle[5] = {0}, o_rank[5] = {0}, o_leaf[5] = {0}, o_sib[5] = {0};
+    int n_objects = 0, n_nodes = 0;
+};
+
+// one device's copy of a committed scene
 struct DeviceScene {
+    int device = -1;
+    int sm_count = 0;
     unsigned char* base = nullptr;
-    size_t bytes_alloc = 0;
     SceneView view;
-    SmemLayout smem;
-    uint64_t bytes = 0;
     unsigned long long* hrpp_keys = nullptr;  // n_predictors x slots
     uint32_t* hrpp_leaves = nullptr;           // n_predictors x slots x HRPP_LEAVES
     size_t hrpp_slots_total = 0;
-    int n_predictors = 0;
     void release() {
+        if (!base && !hrpp_keys && !hrpp_leaves) return;
+        DeviceGuard g;
+        if (g.enter(device) != cudaSuccess) return;
         if (base) cudaFree(base);
         if (hrpp_keys) cudaFree(hrpp_keys);
         if (hrpp_leaves) cudaFree(hrpp_leaves);
-        base = nullptr; hrpp_keys = nullptr; hrpp_leaves = nullptr; bytes_alloc = 0; hrpp_slots_total = 0;
+        base = nullptr; hrpp_keys = nullptr; hrpp_leaves = nullptr; hrpp_slots_total = 0;
     }
 };
 
+// The wavefront pool of one device (queues, counters, framebuffer sums, graphs): per device, not per scene — scenes
+// come and go (one per render call in the e2e path) while the pool is reused.  It grows to the largest render seen
+// and is released by shim_shutdown().
 struct Wavefront {
-    uint32_t pool = 0;
-    DevBuf<f4> ray_o[2], ray_d[2], thr[2], mq_o, mq_d, mq_thr, mq_hit;
+    std::mutex render_mutex;                       // one render in flight per device (constant-memory parameters, shared pool)
+    bool ready = false;
+    int device = -1, sm_count = 0, max_smem = 0;
+    DevBuf<f4> ray_o[2], ray_d[2], thr[2];         // ray queues: wavefront pipeline only
+    DevBuf<f4> mq_o, mq_d, mq_thr, mq_hit;          // material queues (sets x regions x pool entries)
     DevBuf<uint32_t> cnt;
-    DevBuf<float> accum, d_out;
-    float* h_out = nullptr;  // pinned staging for the host framebuffer
+    DevBuf<float> accum, d_out, d_peer;
+    float* h_out = nullptr;  // pinned staging for a pageable host framebuffer
     size_t h_out_n = 0;
     DevBuf<uint32_t> pix_table;
     int pt_key[6] = {0, 0, 0, 0, 0, 0};
     uint32_t npix = 0;
-    uint32_t* h_flags = nullptr;  // pinned: done flag readbacks
+    uint32_t* h_flags = nullptr;  // pinned: done flag / counter readbacks
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr};
-    int grid_extend_smem = 0, grid_extend_gmem = 0, grid_shade = 0, grid_generate = 0, grid_tail = 0;
-    int max_smem = 0;
-    std::mutex render_mutex;                       // one render in flight per device (constant-memory parameters, shared pool)
+    int grid_extend_gmem = 0, grid_extend_gmem_bvh1 = 0, grid_shade = 0, grid_generate = 0, grid_tail = 0;
     cudaStream_t capture_stream = nullptr;         // graphs are captured here (the caller's stream may be the legacy default stream)
+    cudaStream_t work_stream = nullptr;            // shim_render_multi renders on it
     struct LoopGraph { cudaGraphExec_t exec; unsigned long long handle; };
-    std::map<uint64_t, LoopGraph> graphs;          // the whole wavefront loop as one graph (WHILE node), per kernel-variant key
-    std::vector<cudaEvent_t> prof;  // event pairs around wf_extend launches (SHIM_RENDER_PROFILE)
+    typedef std::tuple<uint32_t, int, int, int, int, int, int, int, int, int, int, int> GraphKey;
+    std::map<GraphKey, LoopGraph> graphs;          // the whole wavefront loop as one graph (WHILE node), per kernel-variant key
+    std::vector<cudaEvent_t> prof;                 // event pairs around the launches of an iteration (SHIM_RENDER_PROFILE)
     std::vector<cudaEvent_t> ev_d2h;
-    void release() {
+    size_t pool_bytes() const {
+        size_t b = mq_o.bytes() + mq_d.bytes() + mq_thr.bytes() + mq_hit.bytes() + cnt.bytes() + accum.bytes() + d_out.bytes() + d_peer.bytes() +
+                   pix_table.bytes();
+        for (int i = 0; i < 2; ++i) b += ray_o[i].bytes() + ray_d[i].bytes() + thr[i].bytes();
+        return b;
+    }
+    void release() {   // with the device current
         for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); }
         mq_o.release(); mq_d.release(); mq_thr.release(); mq_hit.release(); cnt.release(); accum.release(); pix_table.release();
+        d_out.release(); d_peer.release();
         if (h_flags) cudaFreeHost(h_flags);
         if (h_out) cudaFreeHost(h_out);
-        h_out = nullptr; h_out_n = 0; d_out.release();
-        h_flags = nullptr;
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-        for (auto& e : ev_chunk) if (e) cudaEventDestroy(e);
-        ev0 = ev1 = ev_chunk[0] = ev_chunk[1] = nullptr;
+        h_out = nullptr; h_out_n = 0; h_flags = nullptr;
+        for (cudaEvent_t* e : {&ev0, &ev1, &ev_chunk[0], &ev_chunk[1]}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
         for (auto& e : prof) cudaEventDestroy(e);
         prof.clear();
-        pool = 0;
+        for (auto& e : ev_d2h) cudaEventDestroy(e);
+        ev_d2h.clear();
+        for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+        graphs.clear();
+        if (capture_stream) cudaStreamDestroy(capture_stream);
+        if (work_stream) cudaStreamDestroy(work_stream);
+        capture_stream = work_stream = nullptr;
+        memset(pt_key, 0, sizeof pt_key);
+        npix = 0;
+        ready = false;
     }
 };
 
+enum { SHIM_MAX_DEVICES = 64 };
+Wavefront g_wf[SHIM_MAX_DEVICES];
+
 }  // namespace
 
+// what a committed scene owns on the device side: the host blob and one DeviceScene per device it has been used on
 struct shim::DeviceState {
-    DeviceScene scene;
-    int device = -1;
-    int sm_count = 0;
+    SceneBlob blob;
+    SmemLayout smem;
+    int n_predictors = 0, hrpp_log2 = 21;
+    int primary = -1;                  // the device shim_commit uploaded to
+    uint32_t kinds_mask = 0;           // material kinds the scene holds (bit k = MatKind k)
+    std::mutex m;                      // guards `on`
+    std::map<int, std::unique_ptr<DeviceScene>> on;
+    ~DeviceState() { for (auto& kv : on) kv.second->release(); }
 };
-void shim::device_state_release(DeviceState* d) {
-    if (!d) return;
-    d->scene.release();
-    delete d;
-}
-
-// The wavefront pool (ray queues, hit buffer, material queues, counters) is per device, not per
-// scene: scenes come and go (one per render call in the e2e path) while the pool is reused.
-static Wavefront g_wf[64];
+void shim::device_state_release(DeviceState* d) { delete d; }
 
 // ------------------------------------------------------------------------------------------ commit
-static int ensure_device(shim_scene* s) {
-    if (!s->dev) s->dev = new DeviceState();
+static int device_count_or_error() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
         return set_err(SHIM_ERR_CUDA, std::string("no usable CUDA device (this backend has no CPU fallback): ") +
                                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
-    CU(cudaGetDevice(&s->dev->device));
-    CU(cudaDeviceGetAttribute(&s->dev->sm_count, cudaDevAttrMultiProcessorCount, s->dev->device));
+    return n;
+}
+
+// uploads the blob to the CURRENT device (which must be `device`) and registers the copy
+static int upload_scene(shim::DeviceState* st, int device, DeviceScene** out) {
+    std::lock_guard<std::mutex> lock(st->m);
+    auto it = st->on.find(device);
+    if (it != st->on.end()) { *out = it->second.get(); return SHIM_OK; }
+    std::unique_ptr<DeviceScene> d(new DeviceScene());
+    d->device = device;
+    CU(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device));
+    const SceneBlob& b = st->blob;
+    CU(cudaMalloc(&d->base, b.bytes.size()));
+    cudaError_t e = cudaMemcpy(d->base, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d->base); d->base = nullptr; return set_err(SHIM_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e)); }
+    SceneView& v = d->view;
+    memset(&v, 0, sizeof v);
+    unsigned char* base = d->base;
+    v.nodes = (const DevNode*)(base + b.o_nodes); v.sph = (const double*)(base + b.o_sph); v.sph_s = (const f4*)(base + b.o_sph_s);
+    v.sph_mat = (const int*)(base + b.o_sph_mat); v.msph = (const f4*)(base + b.o_msph); v.rect = (const f4*)(base + b.o_rect);
+    v.tri = (const f4*)(base + b.o_tri); v.cube = (const f4*)(base + b.o_cube); v.objects = (const DevObject*)(base + b.o_obj);
+    v.materials = (const f4*)(base + b.o_mat); v.textures = (const f4*)(base + b.o_tex);
+    v.images = base + b.o_img; v.perlin = base + b.o_perlin;
+    for (int i = 0; i < 5; ++i) {
+        v.handle[i] = (const int*)(base + b.o_handle[i]); v.rank[i] = (const int*)(base + b.o_rank[i]); v.leaf[i] = (const int*)(base + b.o_leaf[i]);
+        v.sibling[i] = (const int*)(base + b.o_sib[i]);
+    }
+    v.n_objects = b.n_objects; v.n_nodes = b.n_nodes;
+    if (st->n_predictors > 0) {  // one open-addressing table per predictor (cleared at the start of every render that uses them)
+        const int log2 = st->hrpp_log2;
+        d->hrpp_slots_total = ((size_t)1 << log2) * (size_t)st->n_predictors;
+        cudaError_t e1 = cudaMalloc(&d->hrpp_keys, d->hrpp_slots_total * sizeof(unsigned long long));
+        cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&d->hrpp_leaves, d->hrpp_slots_total * HRPP_LEAVES * sizeof(uint32_t)) : e1;
+        if (e2 != cudaSuccess) { d->release(); return set_err(SHIM_ERR_CUDA, std::string("predictor tables: ") + cudaGetErrorString(e2)); }
+        v.hrpp_keys = d->hrpp_keys; v.hrpp_leaves = d->hrpp_leaves; v.hrpp_mask = (uint32_t)(((size_t)1 << log2) - 1); v.hrpp_log2 = log2;
+    }
+    *out = d.get();
+    st->on[device] = std::move(d);
     return SHIM_OK;
 }
 
@@ -150,66 +233,48 @@ SHIM_API int shim_commit(shim_scene* s) {
     if (rc < 0) return set_err(rc, s->sb.err);
     lap("flatten");
     if (s->flat.objects.size() > 65535) return set_err(SHIM_ERR_UNSUPPORTED, "more than 65535 top-level objects");
-    rc = ensure_device(s);
+    rc = device_count_or_error();
     if (rc < 0) return rc;
+    int device = -1;
+    CU(cudaGetDevice(&device));
+    if (device < 0 || device >= SHIM_MAX_DEVICES) return set_err(SHIM_ERR_UNSUPPORTED, "device ordinal out of range");
     const FlatScene& f = s->flat;
-    DeviceScene& d = s->dev->scene;
-    std::vector<unsigned char> blob;
+    if (s->dev) { device_state_release(s->dev); s->dev = nullptr; }
+    std::unique_ptr<shim::DeviceState> st(new shim::DeviceState());
+    SceneBlob& b = st->blob;
     auto put = [&](const void* src, size_t bytes) -> size_t {
-        size_t off = (blob.size() + 255) & ~(size_t)255;
-        blob.resize(off + (bytes ? bytes : 16));
-        if (bytes) memcpy(blob.data() + off, src, bytes);
+        size_t off = (b.bytes.size() + 255) & ~(size_t)255;
+        b.bytes.resize(off + (bytes ? bytes : 16));
+        if (bytes) memcpy(b.bytes.data() + off, src, bytes);
         return off;
     };
-    size_t o_nodes = put(f.nodes.data(), f.nodes.size() * sizeof(DevNode));
-    size_t o_sph = put(f.sph.data(), f.sph.size() * 8), o_sph_s = put(f.sph_s.data(), f.sph_s.size() * 16);
-    size_t o_sph_mat = put(f.sph_mat.data(), f.sph_mat.size() * 4);
-    size_t o_msph = put(f.msph.data(), f.msph.size() * 16), o_rect = put(f.rect.data(), f.rect.size() * 16);
-    size_t o_tri = put(f.tri.data(), f.tri.size() * 16), o_cube = put(f.cube.data(), f.cube.size() * 16);
-    size_t o_obj = put(f.objects.data(), f.objects.size() * sizeof(DevObject));
-    size_t o_mat = put(f.materials.data(), f.materials.size() * 16), o_tex = put(f.textures.data(), f.textures.size() * 16);
-    size_t o_img = put(f.images.data(), f.images.size()), o_perlin = put(f.perlin.data(), f.perlin.size());
-    size_t o_handle[5], o_rank[5], o_leaf[5], o_sib[5];
+    b.o_nodes = put(f.nodes.data(), f.nodes.size() * sizeof(DevNode));
+    b.o_sph = put(f.sph.data(), f.sph.size() * 8); b.o_sph_s = put(f.sph_s.data(), f.sph_s.size() * 16);
+    b.o_sph_mat = put(f.sph_mat.data(), f.sph_mat.size() * 4);
+    b.o_msph = put(f.msph.data(), f.msph.size() * 16); b.o_rect = put(f.rect.data(), f.rect.size() * 16);
+    b.o_tri = put(f.tri.data(), f.tri.size() * 16); b.o_cube = put(f.cube.data(), f.cube.size() * 16);
+    b.o_obj = put(f.objects.data(), f.objects.size() * sizeof(DevObject));
+    b.o_mat = put(f.materials.data(), f.materials.size() * 16); b.o_tex = put(f.textures.data(), f.textures.size() * 16);
+    b.o_img = put(f.images.data(), f.images.size()); b.o_perlin = put(f.perlin.data(), f.perlin.size());
     for (int i = 0; i < 5; ++i) {
-        o_handle[i] = put(f.handle[i].data(), f.handle[i].size() * 4);
-        o_rank[i] = put(f.rank[i].data(), f.rank[i].size() * 4);
-        o_leaf[i] = put(f.leaf[i].data(), f.leaf[i].size() * 4);
-        o_sib[i] = put(f.sibling[i].data(), f.sibling[i].size() * 4);
+        b.o_handle[i] = put(f.handle[i].data(), f.handle[i].size() * 4);
+        b.o_rank[i] = put(f.rank[i].data(), f.rank[i].size() * 4);
+        b.o_leaf[i] = put(f.leaf[i].data(), f.leaf[i].size() * 4);
+        b.o_sib[i] = put(f.sibling[i].data(), f.sibling[i].size() * 4);
     }
+    b.n_objects = (int)f.objects.size(); b.n_nodes = (int)f.nodes.size();
     lap("blob");
-    d.release();
-    CU(cudaMalloc(&d.base, blob.size()));
-    d.bytes_alloc = blob.size();
-    lap("malloc");
-    CU(cudaMemcpy(d.base, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-    lap("memcpy");
-    SceneView& v = d.view;
-    memset(&v, 0, sizeof v);
-    v.nodes = (const DevNode*)(d.base + o_nodes); v.sph = (const double*)(d.base + o_sph); v.sph_s = (const f4*)(d.base + o_sph_s);
-    v.sph_mat = (const int*)(d.base + o_sph_mat); v.msph = (const f4*)(d.base + o_msph); v.rect = (const f4*)(d.base + o_rect);
-    v.tri = (const f4*)(d.base + o_tri); v.cube = (const f4*)(d.base + o_cube); v.objects = (const DevObject*)(d.base + o_obj);
-    v.materials = (const f4*)(d.base + o_mat); v.textures = (const f4*)(d.base + o_tex);
-    v.images = d.base + o_img; v.perlin = d.base + o_perlin;
-    for (int i = 0; i < 5; ++i) {
-        v.handle[i] = (const int*)(d.base + o_handle[i]); v.rank[i] = (const int*)(d.base + o_rank[i]); v.leaf[i] = (const int*)(d.base + o_leaf[i]);
-        v.sibling[i] = (const int*)(d.base + o_sib[i]);
+    st->n_predictors = (int)f.predictor_bvh.size();
+    if (const char* e = getenv("SHIM_HRPP_LOG2")) { int x = atoi(e); if (x >= 8 && x <= 26) st->hrpp_log2 = x; }
+    for (size_t i = 0; i + 1 < f.materials.size(); i += 2) {
+        const int kind = f2i(f.materials[i].x);
+        if (kind >= 0 && kind < MAT_KINDS) st->kinds_mask |= 1u << kind;
     }
-    v.n_objects = (int)f.objects.size(); v.n_nodes = (int)f.nodes.size();
-    d.n_predictors = (int)f.predictor_bvh.size();
-    if (d.n_predictors > 0) {  // one open-addressing table per predictor (cleared at the start of every render that uses them)
-        int log2 = 21;
-        if (const char* e = getenv("SHIM_HRPP_LOG2")) { int x = atoi(e); if (x >= 8 && x <= 26) log2 = x; }
-        d.hrpp_slots_total = ((size_t)1 << log2) * (size_t)d.n_predictors;
-        CU(cudaMalloc(&d.hrpp_keys, d.hrpp_slots_total * sizeof(unsigned long long)));
-        CU(cudaMalloc(&d.hrpp_leaves, d.hrpp_slots_total * HRPP_LEAVES * sizeof(uint32_t)));
-        v.hrpp_keys = d.hrpp_keys; v.hrpp_leaves = d.hrpp_leaves; v.hrpp_mask = (uint32_t)(((size_t)1 << log2) - 1); v.hrpp_log2 = log2;
-    }
-    d.bytes = f.bytes();
-    {   // shared-memory image of what wf_extend walks; total = 0 when it cannot fit any sm_100a block
-        SmemLayout& L = d.smem;
+    {   // shared-memory image of what the closest-hit kernels walk; total = 0 when it cannot fit any sm_100a block
+        SmemLayout& L = st->smem;
         memset(&L, 0, sizeof L);
         uint32_t off = 0;
-        auto place = [&](uint32_t& o, uint32_t& b, size_t bytes) { o = off; b = (uint32_t)bytes; off += (uint32_t)((bytes + 127) & ~(size_t)127); };
+        auto place = [&](uint32_t& o, uint32_t& by, size_t bytes) { o = off; by = (uint32_t)bytes; off += (uint32_t)((bytes + 127) & ~(size_t)127); };
         size_t tot = f.nodes.size() * sizeof(DevNode) + f.sph.size() * 8 + (f.msph.size() + f.rect.size() + f.tri.size() + f.cube.size()) * 16 +
                      f.objects.size() * sizeof(DevObject) + f.sph_mat.size() * 4 + 16;
         if (tot <= 220 * 1024) {
@@ -224,104 +289,152 @@ SHIM_API int shim_commit(shim_scene* s) {
             L.total = off;
         }
     }
+    st->primary = device;
+    DeviceScene* ds = nullptr;
+    rc = upload_scene(st.get(), device, &ds);
+    if (rc < 0) return rc;
+    lap("upload");
+    s->dev = st.release();
     s->has_media = false;
     for (const DevObject& o : f.objects) if (o.flags & OBJ_MEDIUM) s->has_media = true;
     s->committed = true;
     return SHIM_OK;
 }
 
-// ------------------------------------------------------------------------------------------ render
-static int wf_prepare(shim_scene* s, const shim_render_params& p) {
-    Wavefront& w = g_wf[s->dev->device & 63];
-    uint32_t pool = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 24);
-    const char* env = getenv("SHIM_POOL_PATHS");
-    if (p.pool_paths <= 0 && env && atoi(env) > 0) pool = (uint32_t)atoi(env);
-    pool = (pool + 31u) & ~31u;
-    if (w.pool != pool) {
-        for (int i = 0; i < 2; ++i) { CU(w.ray_o[i].alloc(pool)); CU(w.ray_d[i].alloc(pool)); CU(w.thr[i].alloc(pool)); }
-        // two sets of material queues: the wf_trace pipeline goes from one set to the other (the wavefront pipeline uses set 0)
-        CU(w.mq_o.alloc((size_t)pool * MAT_KINDS * 2)); CU(w.mq_d.alloc((size_t)pool * MAT_KINDS * 2));
-        CU(w.mq_thr.alloc((size_t)pool * MAT_KINDS * 2)); CU(w.mq_hit.alloc((size_t)pool * MAT_KINDS * 2));
-        CU(w.cnt.alloc(CNT_WORDS));
-        if (!w.h_flags) CU(cudaMallocHost(&w.h_flags, 128 * sizeof(uint32_t)));
-        if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); CU(cudaEventCreate(&w.ev_chunk[0])); CU(cudaEventCreate(&w.ev_chunk[1])); }
-        w.pool = pool;
-        int sms = s->dev->sm_count, per_sm = 0;
-        CU(cudaDeviceGetAttribute(&w.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->dev->device));
-        CU(cudaFuncSetAttribute(wf_extend<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_bvh1<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_bvh1<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_bvh1<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_bvh1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        w.grid_extend_smem = sms;  // one persistent block per SM owns the shared-memory copy of the scene
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_extend<false, false, false, false>, SHIM_EXTEND_THREADS, 0));
-        w.grid_extend_gmem = sms * (per_sm > 0 ? per_sm : 1);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_shade, 256, 0));
-        w.grid_shade = sms * (per_sm > 0 ? per_sm : 1);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
-        w.grid_generate = sms * (per_sm > 0 ? per_sm : 1);
-        w.grid_tail = sms * 4;
-#define SHIM_TRACE_ATTR(T) CU(cudaFuncSetAttribute(wf_trace_solo<T, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
-                           CU(cudaFuncSetAttribute(wf_trace_solo<T, PT_SPHERE>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
-        SHIM_TRACE_ATTR(512); SHIM_TRACE_ATTR(640); SHIM_TRACE_ATTR(768); SHIM_TRACE_ATTR(896); SHIM_TRACE_ATTR(1024);
-#undef SHIM_TRACE_ATTR
-#define SHIM_LIST_ATTR(T) CU(cudaFuncSetAttribute(wf_extend_list<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
-                          CU(cudaFuncSetAttribute(wf_extend_list<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
-        SHIM_LIST_ATTR(640); SHIM_LIST_ATTR(768); SHIM_LIST_ATTR(896); SHIM_LIST_ATTR(1024);
-#undef SHIM_LIST_ATTR
-#define SHIM_BVH1_ATTR(T) CU(cudaFuncSetAttribute(wf_extend_bvh1<true, false, T, PT_TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024)); \
-                          CU(cudaFuncSetAttribute(wf_extend_bvh1<false, false, T, PT_TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024))
-        SHIM_BVH1_ATTR(640); SHIM_BVH1_ATTR(768); SHIM_BVH1_ATTR(896); SHIM_BVH1_ATTR(1024);
-#undef SHIM_BVH1_ATTR   // 128-thread blocks, one path per thread: covers the 65536-path trigger in one wave
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, PT_SPHERE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 640, PT_SPHERE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, PT_SPHERE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 768, PT_SPHERE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, PT_SPHERE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 896, PT_SPHERE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, PT_SPHERE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-        CU(cudaFuncSetAttribute(wf_extend_solo<false, 1024, PT_SPHERE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, w.max_smem - 1024));
-    }
-    size_t fb = (size_t)p.width * p.height * 3;
-    if (w.accum.n != fb) CU(w.accum.alloc(fb));
-    int world = p.tile_world > 1 ? p.tile_world : 1;
-    int key[6] = {p.width, p.height, p.tile_width, p.tile_height, world > 1 ? p.tile_rank : 0, world};
-    if (memcmp(key, w.pt_key, sizeof key) != 0) {
-        std::vector<uint32_t> order = tile_pixel_order(p.width, p.height, p.tile_width, p.tile_height, key[4], world);
-        CU(w.pix_table.upload(order));
-        w.npix = (uint32_t)order.size();
-        memcpy(w.pt_key, key, sizeof key);
-    }
+// ------------------------------------------------------------------------------------------ per-device set-up
+template <class K>
+static cudaError_t opt_in_smem(K kernel, int bytes) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+
+// one-time set-up of a device's pool (with the device current and its render_mutex held)
+static int wf_init(Wavefront& w, int device) {
+    if (w.ready) return SHIM_OK;
+    w.device = device;
+    CU(cudaDeviceGetAttribute(&w.sm_count, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaDeviceGetAttribute(&w.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CU(w.cnt.alloc(CNT_WORDS));
+    CU(cudaMallocHost(&w.h_flags, 128 * sizeof(uint32_t)));
+    CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); CU(cudaEventCreate(&w.ev_chunk[0])); CU(cudaEventCreate(&w.ev_chunk[1]));
+    const int dyn = w.max_smem - 1024;
+    CU(opt_in_smem(wf_extend<true, false, false, false>, dyn)); CU(opt_in_smem(wf_extend<true, false, true, false>, dyn));
+    CU(opt_in_smem(wf_extend<true, true, false, false>, dyn));  CU(opt_in_smem(wf_extend<true, true, true, false>, dyn));
+    CU(opt_in_smem(wf_extend<true, false, false, true>, dyn));  CU(opt_in_smem(wf_extend<true, false, true, true>, dyn));
+    CU(opt_in_smem(wf_extend_bvh1<true, false>, dyn));  CU(opt_in_smem(wf_extend_bvh1<true, true>, dyn));
+    CU(opt_in_smem(wf_extend_bvh1<false, false>, dyn)); CU(opt_in_smem(wf_extend_bvh1<false, true>, dyn));
+    CU(opt_in_smem(wf_extend_bvh1<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI>, dyn));
+    CU(opt_in_smem(wf_extend_bvh1<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI>, dyn));
+    CU(opt_in_smem(wf_extend_list<false, SHIM_LIST_THREADS>, dyn)); CU(opt_in_smem(wf_extend_list<true, SHIM_LIST_THREADS>, dyn));
+    CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, false>, dyn));
+    CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, true>, dyn));
+    CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_ANY_THREADS, -1, false>, dyn));
+    CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_ANY_THREADS, -1, true>, dyn));
+    CU(opt_in_smem(wf_trace_solo<SHIM_SOLO_SPHERE_THREADS, PT_SPHERE>, dyn));
+    CU(opt_in_smem(wf_trace_solo<SHIM_SOLO_ANY_THREADS, -1>, dyn));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_extend<false, false, false, false>, SHIM_EXTEND_THREADS, 0));
+    w.grid_extend_gmem = w.sm_count * (per_sm > 0 ? per_sm : 1);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_shade, 256, 0));
+    w.grid_shade = w.sm_count * (per_sm > 0 ? per_sm : 1);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
+    w.grid_generate = w.sm_count * (per_sm > 0 ? per_sm : 1);
+    w.grid_tail = w.sm_count * 4;   // 128-thread blocks, one path per thread: covers the 65536-path trigger in one wave
+    w.ready = true;
     return SHIM_OK;
 }
 
-static void launch_extend(const WfParams& k, int grid, uint32_t smem, cudaStream_t st) {
-    const bool S = smem != 0, C = k.count_nodes != 0, M = k.has_media != 0, H = k.use_hrpp != 0;
+// environment switches (read per render: the tests and the probes under tools/ force kernel variants with them)
+struct Switches {
+    bool no_trace, no_fuse, no_bvh1, no_smem, no_graph, solo_any, no_solo, no_list, no_bvh1_tri, trace;
+    int tail;   // < 0: default
+    long pool;  // <= 0: default
+    static bool on(const char* name) { return getenv(name) != nullptr; }
+    static bool zero(const char* name) { const char* e = getenv(name); return e && atoi(e) == 0; }
+    Switches() {
+        no_trace = on("SHIM_NO_TRACE"); no_fuse = on("SHIM_NO_FUSE"); no_bvh1 = on("SHIM_NO_BVH1"); no_smem = on("SHIM_NO_SMEM");
+        no_graph = on("SHIM_NO_GRAPH"); solo_any = on("SHIM_SOLO_ANY"); no_solo = zero("SHIM_SOLO"); no_list = zero("SHIM_LIST");
+        no_bvh1_tri = zero("SHIM_BVH1_TRI"); trace = on("SHIM_TRACE");
+        const char* t = getenv("SHIM_TAIL"); tail = t ? atoi(t) : -1;
+        const char* p = getenv("SHIM_POOL_PATHS"); pool = p ? atol(p) : 0;
+    }
+};
+
+// which kernels a render of this scene uses
+static void choose_variant(const shim_scene* s, const shim::DeviceState* st, const Wavefront& w, const Switches& sw, WfParams& k, bool* use_smem_out) {
+    const FlatScene& f = s->flat;
+    k.bvh1_index = -1;
+    {   // worlds with exactly one BVH among at least one plain object, no medium, no predictor -> wf_extend_bvh1
+        int n_bvh = 0, idx = -1;
+        for (size_t i = 0; i < f.objects.size(); ++i) if (f.objects[i].kind == OBJ_BVH) { ++n_bvh; idx = (int)i; }
+        if (n_bvh == 1 && f.objects.size() > 1 && !s->has_media && !k.use_hrpp && !sw.no_bvh1) k.bvh1_index = idx;
+    }
+    k.smem = st->smem;
+    const int smem_extra = k.bvh1_index >= 0 ? SHIM_BVH1_SMEM_BYTES : 0;
+    const bool use_smem = k.smem.total != 0 && (int)k.smem.total + smem_extra <= w.max_smem - 1024 && !sw.no_smem;
+    if (!use_smem) k.smem.total = 0;
+    *use_smem_out = use_smem;
+    k.solo = 0; k.solo_only = -1; k.fused_generate = 0; k.trace_pipeline = 0;
+    if (use_smem && !k.count_nodes && !k.use_hrpp && !s->has_media && f.objects.size() == 1 && f.objects[0].kind == OBJ_BVH &&
+        (f.objects[0].flags & ~OBJ_PREDICTOR) == 0 && !sw.no_solo) {
+        const bool spheres_only = f.msph.empty() && f.rect.empty() && f.tri.empty() && f.cube.empty() && !sw.solo_any;
+        k.solo_only = spheres_only ? (int)PT_SPHERE : -1;
+        k.solo = spheres_only ? SHIM_SOLO_SPHERE_THREADS : SHIM_SOLO_ANY_THREADS;   // 72 / 80 registers, no spills
+        k.fused_generate = sw.no_fuse ? 0 : 1;
+        if (!sw.no_trace) { k.trace_pipeline = k.solo; k.fused_generate = 1; }   // wf_generate is not part of this pipeline
+    }
+    k.bvh1_tri_threads = 0;
+    if (k.bvh1_index >= 0 && f.sph_s.empty() && f.msph.empty() && f.cube.empty() && !f.tri.empty() && !sw.no_bvh1_tri) {
+        // plain objects are rects, so every primitive inside the Bvh is a triangle ...
+        bool rects_outside = true;
+        for (size_t i = 0; i < f.objects.size(); ++i)
+            if ((int)i != k.bvh1_index && (f.objects[i].kind != OBJ_PRIM || prim_type((uint32_t)f.objects[i].ref) != PT_RECT)) rects_outside = false;
+        // ... if no rect sits inside it: every rect of the scene is a top-level object
+        size_t top_rects = 0;
+        for (const DevObject& o : f.objects) if (o.kind == OBJ_PRIM) ++top_rects;
+        if (rects_outside && top_rects * 2 == f.rect.size()) k.bvh1_tri_threads = SHIM_BVH1_TRI_THREADS;
+    }
+    k.list_threads = 0;
+    if (use_smem && !k.count_nodes && !k.use_hrpp && f.nodes.empty() && !k.solo && !sw.no_list) k.list_threads = SHIM_LIST_THREADS;
+    k.tail_threshold = sw.tail >= 0 ? (uint32_t)sw.tail : 65536u;   // measured on Book-1: 32 k 3.40 ms, 48 k 3.38, 64 k 3.35, 96 k 3.48
+}
+
+// Sizes the pool for this render and lays the material queues out.  The pool is the number of paths in flight:
+// every sample of the render when that fits (fewest iterations), never more than 2^24.
+static int wf_reserve(Wavefront& w, const shim::DeviceState* st, const shim_render_params& p, const Switches& sw, WfParams& k) {
+    uint64_t want = p.pool_paths > 0 ? (uint64_t)p.pool_paths : (sw.pool > 0 ? (uint64_t)sw.pool : k.total_samples);
+    if (want > (1ull << 24)) want = 1ull << 24;
+    if (want < 1024) want = 1024;
+    const uint32_t pool = (uint32_t)((want + 31ull) & ~31ull);
+    k.pool = pool;
+    // material queues: only the kinds the scene has, two kinds per pool-sized region (one up, one down)
+    int n_kinds = 0;
+    for (int kind = 0; kind < MAT_KINDS; ++kind) {
+        k.mq_first[kind] = 0; k.mq_dir[kind] = 1;
+        if (!(st->kinds_mask & (1u << kind))) continue;
+        const long long region = n_kinds / 2;
+        if (n_kinds % 2 == 0) { k.mq_first[kind] = region * (long long)pool; k.mq_dir[kind] = 1; }
+        else { k.mq_first[kind] = region * (long long)pool + (long long)pool - 1; k.mq_dir[kind] = -1; }
+        ++n_kinds;
+    }
+    const size_t regions = (size_t)((n_kinds + 1) / 2 > 0 ? (n_kinds + 1) / 2 : 1);
+    k.mq_set_stride = (long long)(regions * pool);
+    const size_t sets = k.trace_pipeline ? 2 : 1;   // the trace pipeline goes from one set to the other
+    const size_t mq_entries = sets * regions * pool;
+    CU(w.mq_o.reserve(mq_entries)); CU(w.mq_d.reserve(mq_entries)); CU(w.mq_thr.reserve(mq_entries)); CU(w.mq_hit.reserve(mq_entries));
+    if (!k.trace_pipeline)   // ray queues belong to the wavefront pipeline
+        for (int i = 0; i < 2; ++i) { CU(w.ray_o[i].reserve(pool)); CU(w.ray_d[i].reserve(pool)); CU(w.thr[i].reserve(pool)); }
+    for (int i = 0; i < 2; ++i) { k.ray_o[i] = w.ray_o[i].p; k.ray_d[i] = w.ray_d[i].p; k.thr[i] = w.thr[i].p; }
+    k.mq_o = w.mq_o.p; k.mq_d = w.mq_d.p; k.mq_thr = w.mq_thr.p; k.mq_hit = w.mq_hit.p;
+    return SHIM_OK;
+}
+
+static void launch_extend(const Wavefront& w, const WfParams& k, bool use_smem, cudaStream_t st) {
+    const int grid = use_smem ? w.sm_count : w.grid_extend_gmem;   // one persistent block per SM owns the shared-memory copy of the scene
+    const uint32_t smem = use_smem ? k.smem.total : 0;
+    const bool S = use_smem, C = k.count_nodes != 0, M = k.has_media != 0, H = k.use_hrpp != 0;
     if (k.bvh1_index >= 0) {  // one BVH among plain objects, no medium, no predictor: two-phase variant
         if (k.bvh1_tri_threads && !C) {   // triangle-only tree: no primitive dispatch, more warps
-            const int T = k.bvh1_tri_threads;
-            const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES_T(T);
-#define SHIM_BVH1_T(TT) do { if (S) wf_extend_bvh1<true, false, TT, PT_TRI><<<grid, TT, dyn, st>>>(); else wf_extend_bvh1<false, false, TT, PT_TRI><<<grid, TT, dyn, st>>>(); } while (0)
-            switch (T) {
-            case 640: SHIM_BVH1_T(640); break;
-            case 768: SHIM_BVH1_T(768); break;
-            case 896: SHIM_BVH1_T(896); break;
-            default: SHIM_BVH1_T(1024); break;
-            }
-#undef SHIM_BVH1_T
+            const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES_T(SHIM_BVH1_TRI_THREADS);
+            if (S) wf_extend_bvh1<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<grid, SHIM_BVH1_TRI_THREADS, dyn, st>>>();
+            else wf_extend_bvh1<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<grid, SHIM_BVH1_TRI_THREADS, dyn, st>>>();
             return;
         }
         const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES_T(SHIM_EXTEND_THREADS);
@@ -330,28 +443,18 @@ static void launch_extend(const WfParams& k, int grid, uint32_t smem, cudaStream
         return;
     }
     if (k.list_threads) {   // no Bvh in the world, scene image in shared memory
-#define SHIM_LIST_T(T) do { if (k.has_media) wf_extend_list<true, T><<<grid, T, smem, st>>>(); else wf_extend_list<false, T><<<grid, T, smem, st>>>(); } while (0)
-        switch (k.list_threads) {
-        case 640: SHIM_LIST_T(640); break;
-        case 768: SHIM_LIST_T(768); break;
-        case 896: SHIM_LIST_T(896); break;
-        default: SHIM_LIST_T(1024); break;
-        }
-#undef SHIM_LIST_T
+        if (M) wf_extend_list<true, SHIM_LIST_THREADS><<<grid, SHIM_LIST_THREADS, smem, st>>>();
+        else wf_extend_list<false, SHIM_LIST_THREADS><<<grid, SHIM_LIST_THREADS, smem, st>>>();
         return;
     }
     if (k.solo) {   // one plain Bvh, scene image in shared memory
-#define SHIM_SOLO_T(T) do { if (k.solo_only == PT_SPHERE) { if (k.fused_generate) wf_extend_solo<false, T, PT_SPHERE, true><<<grid, T, smem, st>>>(); \
-                                                           else wf_extend_solo<false, T, PT_SPHERE, false><<<grid, T, smem, st>>>(); } \
-                            else { if (k.fused_generate) wf_extend_solo<false, T, -1, true><<<grid, T, smem, st>>>(); \
-                                   else wf_extend_solo<false, T, -1, false><<<grid, T, smem, st>>>(); } } while (0)
-        switch (k.solo) {
-        case 640: SHIM_SOLO_T(640); break;
-        case 768: SHIM_SOLO_T(768); break;
-        case 896: SHIM_SOLO_T(896); break;
-        default: SHIM_SOLO_T(1024); break;
+        if (k.solo_only == PT_SPHERE) {
+            if (k.fused_generate) wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, true><<<grid, SHIM_SOLO_SPHERE_THREADS, smem, st>>>();
+            else wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, false><<<grid, SHIM_SOLO_SPHERE_THREADS, smem, st>>>();
+        } else {
+            if (k.fused_generate) wf_extend_solo<false, SHIM_SOLO_ANY_THREADS, -1, true><<<grid, SHIM_SOLO_ANY_THREADS, smem, st>>>();
+            else wf_extend_solo<false, SHIM_SOLO_ANY_THREADS, -1, false><<<grid, SHIM_SOLO_ANY_THREADS, smem, st>>>();
         }
-#undef SHIM_SOLO_T
         return;
     }
 #define SHIM_LAUNCH(SS, CC, MM, HH) wf_extend<SS, CC, MM, HH><<<grid, SHIM_EXTEND_THREADS, smem, st>>>()
@@ -365,7 +468,6 @@ static void launch_extend(const WfParams& k, int grid, uint32_t smem, cudaStream
 #undef SHIM_LAUNCH
 }
 
-// one wavefront iteration on `st` (the parameters are already in constant memory, the queue index in the counters)
 static void launch_tail(const Wavefront& w, const WfParams& k, cudaStream_t st) {
     if (k.solo) {
         if (k.solo_only == PT_SPHERE) wf_tail<false, true, PT_SPHERE><<<w.grid_tail, 128, 0, st>>>(); else wf_tail<false, true, -1><<<w.grid_tail, 128, 0, st>>>();
@@ -374,21 +476,13 @@ static void launch_tail(const Wavefront& w, const WfParams& k, cudaStream_t st) 
     if (k.use_hrpp) wf_tail<true><<<w.grid_tail, 128, 0, st>>>(); else wf_tail<false><<<w.grid_tail, 128, 0, st>>>();
 }
 static void launch_trace(const Wavefront& w, const WfParams& k, cudaStream_t st) {
-    const int grid = w.grid_extend_smem;
-    const uint32_t smem = k.smem.total;
-#define SHIM_TRACE_T(T) do { if (k.solo_only == PT_SPHERE) wf_trace_solo<T, PT_SPHERE><<<grid, T, smem, st>>>(); else wf_trace_solo<T, -1><<<grid, T, smem, st>>>(); } while (0)
-    switch (k.trace_pipeline) {
-    case 512: SHIM_TRACE_T(512); break;
-    case 640: SHIM_TRACE_T(640); break;
-    case 768: SHIM_TRACE_T(768); break;
-    case 1024: SHIM_TRACE_T(1024); break;
-    default: SHIM_TRACE_T(896); break;
-    }
-#undef SHIM_TRACE_T
+    if (k.solo_only == PT_SPHERE) wf_trace_solo<SHIM_SOLO_SPHERE_THREADS, PT_SPHERE><<<w.sm_count, SHIM_SOLO_SPHERE_THREADS, k.smem.total, st>>>();
+    else wf_trace_solo<SHIM_SOLO_ANY_THREADS, -1><<<w.sm_count, SHIM_SOLO_ANY_THREADS, k.smem.total, st>>>();
 }
 static void launch_tail_mq(const Wavefront& w, const WfParams& k, cudaStream_t st) {
     if (k.solo_only == PT_SPHERE) wf_tail_mq<PT_SPHERE><<<w.grid_tail, 128, 0, st>>>(); else wf_tail_mq<-1><<<w.grid_tail, 128, 0, st>>>();
 }
+// one wavefront iteration on `st` (the parameters are already in constant memory, the queue index in the counters)
 static void launch_iteration(const Wavefront& w, const WfParams& k, bool use_smem, cudaStream_t st) {
     if (k.trace_pipeline) {   // shade -> closest hit, then endgame / loop condition / counters of the next iteration
         launch_trace(w, k, st);
@@ -396,7 +490,7 @@ static void launch_iteration(const Wavefront& w, const WfParams& k, bool use_sme
         return;
     }
     wf_generate<<<w.grid_generate, 256, 0, st>>>();
-    launch_extend(k, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
+    launch_extend(w, k, use_smem, st);
     wf_shade<<<w.grid_shade, 256, 0, st>>>();
     launch_tail(w, k, st);   // also the loop's condition: done flag / WHILE-node condition
 }
@@ -417,9 +511,9 @@ static bool under_profiler() {
 }
 
 static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
-    uint64_t key = (uint64_t)(use_smem ? k.smem.total : 0) | ((uint64_t)(k.count_nodes != 0) << 32) | ((uint64_t)(k.has_media != 0) << 33) |
-                   ((uint64_t)(k.use_hrpp != 0) << 34) | ((uint64_t)use_smem << 36) | ((uint64_t)(k.bvh1_index >= 0) << 37) |
-                   ((uint64_t)(k.bvh1_index >= 0 ? (uint32_t)k.bvh1_index & 0xffffu : 0u) << 40) | ((uint64_t)(uint32_t)k.solo << 48) | ((uint64_t)(k.solo && k.solo_only == PT_SPHERE) << 39) | ((uint64_t)((uint32_t)k.list_threads / 128u) << 60) | ((uint64_t)(k.fused_generate != 0) << 38) | ((uint64_t)((uint32_t)k.trace_pipeline / 128u) << 44) | ((uint64_t)((uint32_t)k.bvh1_tri_threads / 128u) << 52);
+    // everything launch_iteration branches on (the launches themselves take no arguments)
+    const Wavefront::GraphKey key(use_smem ? k.smem.total : 0u, use_smem ? 1 : 0, k.count_nodes != 0, k.has_media != 0, k.use_hrpp != 0,
+                                  k.bvh1_index >= 0, k.bvh1_tri_threads, k.list_threads, k.solo, k.solo_only, k.fused_generate, k.trace_pipeline);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));
@@ -447,101 +541,66 @@ static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront:
     return SHIM_OK;
 }
 
-SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shim_render_params* pp, float* d_out, shim_stats* stats,
-                                void* cuda_stream) {
-    NEED(s);
+static int check_render_params(const shim_scene* s, const shim_camera* cam, const shim_render_params* pp, const void* out) {
     if (!s->committed) return set_err(SHIM_ERR_STATE, "shim_render: scene not committed");
-    if (!cam || !pp || !d_out) return set_err(SHIM_ERR_INVALID, "shim_render: null argument");
+    if (!cam || !pp || !out) return set_err(SHIM_ERR_INVALID, "shim_render: null argument");
     const shim_render_params& p = *pp;
     if (p.width < 2 || p.height < 2 || p.samples_per_pixel < 1 || p.tile_width < 1 || p.tile_height < 1 || p.max_depth < 0 ||
-        p.sample_count < 0 || p.sample_begin < 0 || (p.tile_world > 1 && (p.tile_rank < 0 || p.tile_rank >= p.tile_world)))
+        p.sample_count < -1 || p.sample_begin < 0 || (p.tile_world > 1 && (p.tile_rank < 0 || p.tile_rank >= p.tile_world)))
         return set_err(SHIM_ERR_INVALID, "shim_render: bad render params");
     if ((uint64_t)p.width * (uint64_t)p.height > 0x7fffffffull) return set_err(SHIM_ERR_INVALID, "shim_render: image too large");
     if (p.max_depth > 255) return set_err(SHIM_ERR_UNSUPPORTED, "shim_render: max_depth above 255 (the bounce is carried in 8 bits of the ray record)");
     if ((int64_t)p.sample_begin + (p.sample_count > 0 ? p.sample_count : p.samples_per_pixel) > (1 << 24))
         return set_err(SHIM_ERR_UNSUPPORTED, "shim_render: absolute sample index above 2^24 (carried in 24 bits of the ray record)");
-    {   // the scene's arrays, the pool and the constant-memory parameters all belong to the device the scene was committed on
-        int cur_dev = -1;
-        CU(cudaGetDevice(&cur_dev));
-        if (cur_dev != s->dev->device)
-            return set_err(SHIM_ERR_STATE, "shim_render: the scene was committed on CUDA device " + std::to_string(s->dev->device) +
-                                               " but the current device is " + std::to_string(cur_dev));
-    }
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    int rc = wf_prepare(s, p);
+    if ((p.flags & SHIM_RENDER_COUNT_NODES) && (p.flags & SHIM_RENDER_PREDICTORS) && s->dev->n_predictors > 0)
+        return set_err(SHIM_ERR_INVALID, "shim_render: SHIM_RENDER_COUNT_NODES cannot be combined with SHIM_RENDER_PREDICTORS");
+    return SHIM_OK;
+}
+
+// The render proper: device `w.device` is current, w.render_mutex is held, `ds` is the scene's copy on that device.
+// Enqueues everything on `st`, waits for it, fills `stats`.
+static int render_locked(shim_scene* s, DeviceScene& ds, Wavefront& w, const shim_camera* cam, const shim_render_params& p, float* d_out,
+                         shim_stats* stats, cudaStream_t st) {
+    int rc = wf_init(w, ds.device);
     if (rc < 0) return rc;
-    Wavefront& w = g_wf[s->dev->device & 63];
-    std::lock_guard<std::mutex> render_lock(w.render_mutex);
+    const Switches sw;
+    const size_t fb = (size_t)p.width * p.height * 3;
+    CU(w.accum.reserve(fb));
+    const int world = p.tile_world > 1 ? p.tile_world : 1;
+    const int key[6] = {p.width, p.height, p.tile_width, p.tile_height, world > 1 ? p.tile_rank : 0, world};
+    if (memcmp(key, w.pt_key, sizeof key) != 0) {
+        std::vector<uint32_t> order = tile_pixel_order(p.width, p.height, p.tile_width, p.tile_height, key[4], world);
+        memset(w.pt_key, 0, sizeof w.pt_key);
+        CU(w.pix_table.upload(order));
+        w.npix = (uint32_t)order.size();
+        memcpy(w.pt_key, key, sizeof key);
+    }
 
     WfParams k;
     memset(&k, 0, sizeof k);
-    k.sv = s->dev->scene.view;
+    k.sv = ds.view;
     camera_new(cam->look_from, cam->look_at, cam->view_up, cam->vertical_fov, cam->aspect_ratio, cam->aperture, cam->focus_dist,
                cam->time_start, cam->time_end, k.cam);
-    for (int i = 0; i < 2; ++i) { k.ray_o[i] = w.ray_o[i].p; k.ray_d[i] = w.ray_d[i].p; k.thr[i] = w.thr[i].p; }
-    k.mq_o = w.mq_o.p; k.mq_d = w.mq_d.p; k.mq_thr = w.mq_thr.p; k.mq_hit = w.mq_hit.p;
     k.cnt = w.cnt.p; k.accum = w.accum.p; k.pix_table = w.pix_table.p;
     k.npix = w.npix;
-    int count = p.sample_count > 0 ? p.sample_count : p.samples_per_pixel;
+    // sample_count: 0 = every sample of the image, -1 = none (a shard that owns no samples), n = that many from sample_begin
+    const int count = p.sample_count > 0 ? p.sample_count : (p.sample_count < 0 ? 0 : p.samples_per_pixel);
     k.total_samples = (uint64_t)w.npix * (uint64_t)count;
-    k.pool = w.pool; k.width = p.width; k.height = p.height; k.max_depth = p.max_depth; k.sample_begin = p.sample_begin;
+    k.width = p.width; k.height = p.height; k.max_depth = p.max_depth; k.sample_begin = p.sample_begin;
     k.bg[0] = p.background[0]; k.bg[1] = p.background[1]; k.bg[2] = p.background[2];
     k.seed = p.seed; k.has_media = s->has_media ? 1 : 0; k.count_nodes = (p.flags & SHIM_RENDER_COUNT_NODES) ? 1 : 0;
-    k.use_hrpp = ((p.flags & SHIM_RENDER_PREDICTORS) && s->dev->scene.n_predictors > 0) ? 1 : 0;
+    k.use_hrpp = ((p.flags & SHIM_RENDER_PREDICTORS) && s->dev->n_predictors > 0) ? 1 : 0;
     if (k.use_hrpp) {  // a fresh Predictor per render (bvh.rs:69-81 builds them with the scene)
-        if (k.count_nodes) return set_err(SHIM_ERR_INVALID, "shim_render: SHIM_RENDER_COUNT_NODES cannot be combined with SHIM_RENDER_PREDICTORS");
-        CU(cudaMemsetAsync(s->dev->scene.hrpp_keys, 0, s->dev->scene.hrpp_slots_total * sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(s->dev->scene.hrpp_leaves, 0xFF, s->dev->scene.hrpp_slots_total * HRPP_LEAVES * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(ds.hrpp_keys, 0, ds.hrpp_slots_total * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(ds.hrpp_leaves, 0xFF, ds.hrpp_slots_total * HRPP_LEAVES * sizeof(uint32_t), st));
     }
-    k.bvh1_index = -1;
-    {   // worlds with exactly one BVH among at least one plain object, no medium, no predictor -> wf_extend_bvh1
-        int n_bvh = 0, idx = -1;
-        for (size_t i = 0; i < s->flat.objects.size(); ++i) if (s->flat.objects[i].kind == OBJ_BVH) { ++n_bvh; idx = (int)i; }
-        if (n_bvh == 1 && s->flat.objects.size() > 1 && !s->has_media && !k.use_hrpp && !getenv("SHIM_NO_BVH1")) k.bvh1_index = idx;
-    }
-    k.smem = s->dev->scene.smem;
-    const int smem_extra = k.bvh1_index >= 0 ? SHIM_BVH1_SMEM_BYTES : 0;
-    const bool use_smem = k.smem.total != 0 && (int)k.smem.total + smem_extra <= w.max_smem - 1024 && !getenv("SHIM_NO_SMEM");
-    if (!use_smem) k.smem.total = 0;
-    k.solo = 0;
-    if (use_smem && !k.count_nodes && !k.use_hrpp && !s->has_media && s->flat.objects.size() == 1 && s->flat.objects[0].kind == OBJ_BVH &&
-        (s->flat.objects[0].flags & ~OBJ_PREDICTOR) == 0) {
-        const FlatScene& f = s->flat;
-        const bool spheres_only = f.msph.empty() && f.rect.empty() && f.tri.empty() && f.cube.empty() && !getenv("SHIM_SOLO_ANY");
-        k.solo_only = spheres_only ? (int)PT_SPHERE : -1;
-        k.solo = spheres_only ? 896 : 768;   // 72 / 80 registers, no spills (measured: 3.15 / 3.21 ms on Book-1, 3.56 ms with wf_extend)
-        if (const char* e = getenv("SHIM_SOLO")) k.solo = atoi(e);
-        k.fused_generate = (k.solo && !getenv("SHIM_NO_FUSE")) ? 1 : 0;
-        if (k.solo && !getenv("SHIM_NO_TRACE")) {
-            k.trace_pipeline = spheres_only ? 896 : 768;   // Book-1: 3.00 ms wavefront, 3.28 / 3.00 / 2.92 / 2.91 ms at 512 / 640 / 768 / 896 threads
-            if (const char* e = getenv("SHIM_TRACE_T")) k.trace_pipeline = atoi(e);
-            if (k.trace_pipeline) k.fused_generate = 1;   // wf_generate only publishes counters in this pipeline
-        }
-    }
-    k.bvh1_tri_threads = 0;
-    if (k.bvh1_index >= 0 && s->flat.sph_s.empty() && s->flat.msph.empty() && s->flat.cube.empty() && !s->flat.tri.empty()) {
-        // plain objects are rects, so every primitive inside the Bvh is a triangle
-        bool rects_outside = true;
-        for (size_t i = 0; i < s->flat.objects.size(); ++i)
-            if ((int)i != k.bvh1_index && (s->flat.objects[i].kind != OBJ_PRIM || prim_type((uint32_t)s->flat.objects[i].ref) != PT_RECT)) rects_outside = false;
-        // ... and no rect inside it: every rect of the scene is a top-level object
-        size_t top_rects = 0;
-        for (const DevObject& o : s->flat.objects) if (o.kind == OBJ_PRIM) ++top_rects;
-        if (rects_outside && top_rects * 2 == s->flat.rect.size()) {
-            k.bvh1_tri_threads = 896;   // bunny / igea stand-ins: 43.8 / 70.7 ms generic, 39.7 / 62.9 ms at 896 threads (768: 40.9 / 65.9)
-            if (const char* e = getenv("SHIM_BVH1_TRI")) k.bvh1_tri_threads = atoi(e);
-        }
-    }
-    k.list_threads = 0;
-    if (use_smem && !k.count_nodes && !k.use_hrpp && s->flat.nodes.empty() && !k.solo) {
-        k.list_threads = 1024;   // cornell-smoke, 64 spp: 18.3 ms with wf_extend, 16.4 / 15.4 / 15.0 / 14.9 ms at 640 / 768 / 896 / 1024 threads
-        if (const char* e = getenv("SHIM_LIST")) k.list_threads = atoi(e);
-    }
-    k.tail_threshold = 65536;   // measured on Book-1: 32 k 3.40 ms, 48 k 3.38, 64 k 3.35, 96 k 3.48 (the grid covers 75 k paths)
-    if (const char* e = getenv("SHIM_TAIL")) k.tail_threshold = (uint32_t)atoi(e);
+    bool use_smem = false;
+    choose_variant(s, s->dev, w, sw, k, &use_smem);
+    rc = wf_reserve(w, s->dev, p, sw, k);
+    if (rc < 0) return rc;
 
     CU(cudaMemsetAsync(w.cnt.p, 0, CNT_WORDS * sizeof(uint32_t), st));
-    CU(cudaMemsetAsync(w.accum.p, 0, w.accum.n * sizeof(float), st));
+    CU(cudaMemsetAsync(w.accum.p, 0, fb * sizeof(float), st));
     CU(cudaEventRecord(w.ev0, st));
 
     const bool profile = (p.flags & SHIM_RENDER_PROFILE) != 0;
@@ -555,7 +614,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
     k.max_iterations = 1u << 30;
     const bool run = k.total_samples > 0 && p.max_depth > 0;
     // Without per-kernel events the loop is ONE graph launch (WHILE node, condition set by wf_tail on the device).
-    const bool use_graph = run && !profile && !getenv("SHIM_NO_GRAPH") && !under_profiler();
+    const bool use_graph = run && !profile && !sw.no_graph && !under_profiler();
     Wavefront::LoopGraph lg{nullptr, 0ull};
     if (use_graph) { int grc = loop_graph(w, k, use_smem, &lg); if (grc < 0) return grc; }
     k.loop_handle = lg.handle;
@@ -575,7 +634,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
                 if (!k.trace_pipeline) wf_generate<<<w.grid_generate, 256, 0, st>>>();
                 if (rec) CU(cudaEventRecord(w.prof[prof_used + 1], st));
                 if (k.trace_pipeline) launch_trace(w, k, st);
-                else launch_extend(k, use_smem ? w.grid_extend_smem : w.grid_extend_gmem, use_smem ? k.smem.total : 0, st);
+                else launch_extend(w, k, use_smem, st);
                 if (rec) CU(cudaEventRecord(w.prof[prof_used + 2], st));
                 if (k.trace_pipeline) launch_tail_mq(w, k, st);
                 else { wf_shade<<<w.grid_shade, 256, 0, st>>>(); launch_tail(w, k, st); }
@@ -592,8 +651,7 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
             if (c > (1 << 24)) return set_err(SHIM_ERR_CUDA, "wavefront did not terminate");
         }
     }
-    size_t fb = (size_t)p.width * p.height * 3;
-    wf_finalize<<<s->dev->sm_count * 4, 256, 0, st>>>(w.accum.p, d_out, fb, (float)p.samples_per_pixel, (p.flags & SHIM_RENDER_RAW_SUM) ? 1 : 0);
+    wf_finalize<<<w.sm_count * 4, 256, 0, st>>>(w.accum.p, d_out, fb, (float)p.samples_per_pixel, (p.flags & SHIM_RENDER_RAW_SUM) ? 1 : 0);
     CU(cudaEventRecord(w.ev1, st));
     CU(cudaMemcpyAsync(w.h_flags + 32, w.cnt.p, CNT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -610,15 +668,17 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
         stats->hrpp_no_prediction = c64[C64_HRPP_NONE];
         stats->iterations = w.h_flags[32 + CNT_ITER];
         stats->extend_variant = k.trace_pipeline ? 4u : k.solo ? 2u : (k.list_threads ? 3u : (k.bvh1_index >= 0 ? 1u : 0u));
-        // four kernels per executed iteration body (the last body may find the queue already empty) + wf_finalize
         // trace pipeline: wf_trace_first + two kernels per iteration body + wf_finalize; wavefront: four per body + wf_finalize
-        stats->kernel_launches = k.trace_pipeline ? 2ull * w.h_flags[32 + CNT_BODIES] + 2ull : 4ull * w.h_flags[32 + CNT_BODIES] + 1ull;
+        // (the last body may find the queue already empty)
+        stats->kernel_launches = !run ? 1ull : (k.trace_pipeline ? 2ull * w.h_flags[32 + CNT_BODIES] + 2ull : 4ull * w.h_flags[32 + CNT_BODIES] + 1ull);
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
         stats->device_ms = ms;
-        // per-launch durations of wf_extend while it had work: launches past the done flag are skipped
+        stats->pool_paths = k.pool;
+        stats->pool_bytes = w.pool_bytes();
+        stats->devices = 1;
+        // per-launch durations of the closest-hit kernel while it had work: launches past the done flag are skipped
         uint64_t it_done = stats->iterations;
-        const bool trace = getenv("SHIM_TRACE") != nullptr;
         for (size_t i = 0; i + 3 < prof_used && i / 4 < it_done; i += 4) {
             float g = 0, e = 0, sh = 0;
             CU(cudaEventElapsedTime(&g, w.prof[i], w.prof[i + 1]));
@@ -628,21 +688,39 @@ SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shi
             stats->extend_ms += e;
             stats->shade_ms += sh;
             stats->extend_launches += 1;
-            if (trace) fprintf(stderr, "shim-trace iter %3zu generate %.4f extend %.4f shade %.4f ms\n", i / 4, g, e, sh);
+            if (sw.trace) fprintf(stderr, "shim-trace iter %3zu generate %.4f extend %.4f shade %.4f ms\n", i / 4, g, e, sh);
         }
     }
     return SHIM_OK;
 }
 
-SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_render_params* p, float* out, shim_stats* stats) {
+// the scene's copy on `device` (the current device), uploaded on first use
+static int scene_on_device(shim_scene* s, int device, DeviceScene** out) {
+    if (device < 0 || device >= SHIM_MAX_DEVICES) return set_err(SHIM_ERR_UNSUPPORTED, "device ordinal out of range");
+    return upload_scene(s->dev, device, out);
+}
+
+SHIM_API int shim_render_device(shim_scene* s, const shim_camera* cam, const shim_render_params* pp, float* d_out, shim_stats* stats,
+                                void* cuda_stream) {
     NEED(s);
-    if (!p || !out) return set_err(SHIM_ERR_INVALID, "shim_render: null argument");
-    if (!s->committed) return set_err(SHIM_ERR_STATE, "shim_render: scene not committed");
-    if (p->width < 2 || p->height < 2) return set_err(SHIM_ERR_INVALID, "shim_render: bad render params");
-    size_t fb = (size_t)p->width * p->height * 3;
-    int rc = ensure_device(s);
+    int rc = check_render_params(s, cam, pp, d_out);
     if (rc < 0) return rc;
-    Wavefront& w = g_wf[s->dev->device & 63];
+    // the output buffer and the stream belong to the caller's current device: it has to be the one the scene lives on
+    int cur_dev = -1;
+    CU(cudaGetDevice(&cur_dev));
+    if (cur_dev != s->dev->primary)
+        return set_err(SHIM_ERR_STATE, "shim_render: the scene was committed on CUDA device " + std::to_string(s->dev->primary) +
+                                           " but the current device is " + std::to_string(cur_dev));
+    DeviceScene* ds = nullptr;
+    rc = scene_on_device(s, cur_dev, &ds);
+    if (rc < 0) return rc;
+    Wavefront& w = g_wf[cur_dev];
+    std::lock_guard<std::mutex> render_lock(w.render_mutex);   // before anything touches the shared pool
+    return render_locked(s, *ds, w, cam, *pp, d_out, stats, (cudaStream_t)cuda_stream);
+}
+
+// device framebuffer -> caller's host buffer (with w.render_mutex held: the staging buffers are shared)
+static int copy_out(Wavefront& w, const float* d_src, float* out, size_t fb, cudaStream_t st) {
     // a page-locked destination (shim_host_alloc, or memory the caller registered) takes the D2H directly
     bool pinned_out = false;
     {
@@ -650,12 +728,9 @@ SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_rende
         if (cudaPointerGetAttributes(&at, out) == cudaSuccess) pinned_out = at.type == cudaMemoryTypeHost;
         else cudaGetLastError();
     }
-    if (w.d_out.n < fb) CU(w.d_out.alloc(fb));
     if (pinned_out) {
-        rc = shim_render_device(s, cam, p, w.d_out.p, stats, nullptr);
-        if (rc != SHIM_OK) return rc;
-        CU(cudaMemcpyAsync(out, w.d_out.p, fb * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
-        CU(cudaStreamSynchronize(nullptr));
+        CU(cudaMemcpyAsync(out, d_src, fb * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
         return SHIM_OK;
     }
     // otherwise: persistent pinned staging, no allocation on the per-call path
@@ -665,8 +740,6 @@ SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_rende
         CU(cudaMallocHost(&w.h_out, fb * sizeof(float)));
         w.h_out_n = fb;
     }
-    rc = shim_render_device(s, cam, p, w.d_out.p, stats, nullptr);
-    if (rc != SHIM_OK) return rc;
     // D2H in chunks through the pinned staging buffer; the copy of chunk k into the caller's (pageable) buffer
     // overlaps the D2H of the chunks behind it
     const int chunks = 8;
@@ -674,8 +747,8 @@ SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_rende
     const size_t per = (fb + chunks - 1) / chunks;
     for (int c = 0; c < chunks; ++c) {
         size_t off = (size_t)c * per, cnt = off < fb ? (fb - off < per ? fb - off : per) : 0;
-        if (cnt) CU(cudaMemcpyAsync(w.h_out + off, w.d_out.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
-        CU(cudaEventRecord(w.ev_d2h[c], nullptr));
+        if (cnt) CU(cudaMemcpyAsync(w.h_out + off, d_src + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(w.ev_d2h[c], st));
     }
     // two host threads copy alternate chunks out of the staging buffer as they land (a single memcpy of a 1200x800
     // framebuffer costs about as much as a quarter of the Book-1 render)
@@ -698,6 +771,172 @@ SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_rende
     return SHIM_OK;
 }
 
+SHIM_API int shim_render(shim_scene* s, const shim_camera* cam, const shim_render_params* p, float* out, shim_stats* stats) {
+    NEED(s);
+    int rc = check_render_params(s, cam, p, out);
+    if (rc < 0) return rc;
+    const size_t fb = (size_t)p->width * p->height * 3;
+    // host buffers in, host buffers out: the call runs on the scene's device whatever the caller's current device is
+    DeviceGuard guard;
+    CU(guard.enter(s->dev->primary));
+    DeviceScene* ds = nullptr;
+    rc = scene_on_device(s, s->dev->primary, &ds);
+    if (rc < 0) return rc;
+    Wavefront& w = g_wf[s->dev->primary];
+    std::lock_guard<std::mutex> render_lock(w.render_mutex);   // held across the render AND the copy out of the shared d_out / staging
+    CU(w.d_out.reserve(fb));
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = render_locked(s, *ds, w, cam, *p, w.d_out.p, stats, nullptr);
+    if (rc != SHIM_OK) return rc;
+    rc = copy_out(w, w.d_out.p, out, fb, nullptr);
+    if (stats) stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ one image on several devices
+__global__ void wf_add_inplace(float* acc, const float* part, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc[i] += part[i];
+}
+__global__ void wf_mean_inplace(float* acc, size_t n, float spp) {   // renderer.rs:147, the same division as wf_finalize
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc[i] = acc[i] / spp;
+}
+
+// Renderer::render's tile fan-out (renderer.rs:63-95) across devices instead of threads: the scene is replicated,
+// device i renders its shard (a range of sample indices, or the tiles with index % n == i) with private accumulation
+// on one host thread and one stream per device, and the raw sums are combined ONCE at the end on the first device
+// (peer copies over NVLink + an add kernel) before the mean is taken and copied to the caller's host buffer.
+SHIM_API int shim_render_multi(shim_scene* s, const shim_camera* cam, const shim_render_params* pp, int n_devices, const int* devices,
+                               int mode, float* out, shim_stats* stats) {
+    NEED(s);
+    int rc = check_render_params(s, cam, pp, out);
+    if (rc < 0) return rc;
+    if (mode != SHIM_SHARD_SAMPLES && mode != SHIM_SHARD_TILES) return set_err(SHIM_ERR_INVALID, "shim_render_multi: mode must be SHIM_SHARD_SAMPLES or SHIM_SHARD_TILES");
+    if (pp->tile_world > 1) return set_err(SHIM_ERR_INVALID, "shim_render_multi: the call shards the image itself (tile_world must be 0 or 1)");
+    rc = device_count_or_error();
+    if (rc < 0) return rc;
+    const int have = rc;
+    if (n_devices <= 0) n_devices = have;
+    if (n_devices > have || n_devices > SHIM_MAX_DEVICES) return set_err(SHIM_ERR_INVALID, "shim_render_multi: more devices requested than present");
+    std::vector<int> dev(n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        dev[i] = devices ? devices[i] : i;
+        if (dev[i] < 0 || dev[i] >= have) return set_err(SHIM_ERR_INVALID, "shim_render_multi: bad device ordinal");
+        for (int j = 0; j < i; ++j) if (dev[j] == dev[i]) return set_err(SHIM_ERR_INVALID, "shim_render_multi: device listed twice");
+    }
+    const shim_render_params& p = *pp;
+    const size_t fb = (size_t)p.width * p.height * 3;
+    const int total = p.sample_count > 0 ? p.sample_count : (p.sample_count < 0 ? 0 : p.samples_per_pixel);
+
+    // one multi-device render at a time: each holds several devices' pools until its combine, and two of them taking
+    // the same pools in different orders would wait for each other forever
+    static std::mutex multi_mutex;
+    std::lock_guard<std::mutex> multi_lock(multi_mutex);
+    struct Part { int rc = SHIM_OK; std::string err; shim_stats st; bool rendered = false; };
+    std::vector<Part> part(n_devices);
+    // every device's pool stays locked from its render until the combine has read its sums
+    std::vector<std::unique_lock<std::mutex>> locks(n_devices);
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int i) {
+        Part& me = part[i];
+        memset(&me.st, 0, sizeof me.st);
+        auto fail = [&](int code) { me.rc = code; me.err = shim_last_error(); };
+        if (cudaSetDevice(dev[i]) != cudaSuccess) { me.rc = set_err(SHIM_ERR_CUDA, "cudaSetDevice failed"); me.err = shim_last_error(); return; }
+        shim_render_params q = p;
+        q.flags |= SHIM_RENDER_RAW_SUM;
+        if (mode == SHIM_SHARD_SAMPLES) {   // contiguous ranges of absolute sample indices, the remainder to the first devices
+            const int base = total / n_devices, rem = total % n_devices;
+            const int cnt = base + (i < rem ? 1 : 0);
+            q.sample_begin = p.sample_begin + i * base + (i < rem ? i : rem);
+            q.sample_count = cnt > 0 ? cnt : -1;
+        } else {
+            q.tile_rank = i; q.tile_world = n_devices;
+            q.sample_count = total > 0 ? total : -1;
+        }
+        DeviceScene* ds = nullptr;
+        int r = scene_on_device(s, dev[i], &ds);
+        if (r < 0) return fail(r);
+        Wavefront& w = g_wf[dev[i]];
+        locks[i] = std::unique_lock<std::mutex>(w.render_mutex);
+        if (!w.work_stream && cudaStreamCreateWithFlags(&w.work_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            me.rc = set_err(SHIM_ERR_CUDA, "cudaStreamCreate failed"); me.err = shim_last_error(); return;
+        }
+        if (w.d_out.reserve(fb) != cudaSuccess) { me.rc = set_err(SHIM_ERR_CUDA, "framebuffer allocation failed"); me.err = shim_last_error(); return; }
+        if (i == 0 && n_devices > 1 && w.d_peer.reserve(fb) != cudaSuccess) { me.rc = set_err(SHIM_ERR_CUDA, "peer buffer allocation failed"); me.err = shim_last_error(); return; }
+        r = render_locked(s, *ds, w, cam, q, w.d_out.p, &me.st, w.work_stream);
+        if (r < 0) return fail(r);
+        me.rendered = true;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int i = 1; i < n_devices; ++i) th.emplace_back(work, i);
+        DeviceGuard guard;   // the calling thread renders on the first device and gets its own device back afterwards
+        cudaError_t ge = guard.enter(dev[0]);
+        if (ge == cudaSuccess) work(0); else { part[0].rc = set_err(SHIM_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ge)); part[0].err = shim_last_error(); }
+        for (auto& t : th) t.join();
+        for (int i = 0; i < n_devices; ++i) if (part[i].rc < 0) { locks.clear(); return set_err(part[i].rc, "device " + std::to_string(dev[i]) + ": " + part[i].err); }
+        // ---- the one combine: peer copy of every other device's sums onto the first device, add, mean, copy out
+        Wavefront& w0 = g_wf[dev[0]];
+        cudaStream_t st0 = w0.work_stream;
+        for (int i = 1; i < n_devices; ++i) {
+            Wavefront& wi = g_wf[dev[i]];
+            int can = 0;   // direct NVLink copies where the devices can reach each other (the copy is staged through the host otherwise)
+            if (cudaDeviceCanAccessPeer(&can, dev[0], dev[i]) == cudaSuccess && can) {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(dev[i], 0);
+                if (pe != cudaSuccess) cudaGetLastError();   // already enabled
+            }
+            CU(cudaMemcpyPeerAsync(w0.d_peer.p, dev[0], wi.d_out.p, dev[i], fb * sizeof(float), st0));
+            wf_add_inplace<<<w0.sm_count * 4, 256, 0, st0>>>(w0.d_out.p, w0.d_peer.p, fb);
+        }
+        if (!(p.flags & SHIM_RENDER_RAW_SUM)) wf_mean_inplace<<<w0.sm_count * 4, 256, 0, st0>>>(w0.d_out.p, fb, (float)p.samples_per_pixel);
+        CU(cudaGetLastError());
+        rc = copy_out(w0, w0.d_out.p, out, fb, st0);
+        locks.clear();
+        if (rc < 0) return rc;
+    }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int i = 0; i < n_devices; ++i) {
+            const shim_stats& a = part[i].st;
+            stats->rays += a.rays; stats->samples += a.samples; stats->node_visits += a.node_visits; stats->prim_tests += a.prim_tests;
+            stats->hrpp_true_positive += a.hrpp_true_positive; stats->hrpp_false_positive += a.hrpp_false_positive;
+            stats->hrpp_no_prediction += a.hrpp_no_prediction; stats->kernel_launches += a.kernel_launches;
+            if (a.iterations > stats->iterations) stats->iterations = a.iterations;
+            if (a.device_ms > stats->device_ms) stats->device_ms = a.device_ms;   // the slowest device's loop
+            stats->pool_bytes += a.pool_bytes;
+            if (a.pool_paths > stats->pool_paths) stats->pool_paths = a.pool_paths;
+            stats->extend_variant = a.extend_variant;
+        }
+        stats->kernel_launches += (uint64_t)(n_devices - 1) + ((p.flags & SHIM_RENDER_RAW_SUM) ? 0u : 1u);
+        stats->devices = (uint64_t)n_devices;
+        stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return SHIM_OK;
+}
+
+// frees every device's pool, graphs, events and staging buffers (scenes keep their own arrays until shim_scene_destroy).
+// No render may be in flight.
+SHIM_API int shim_shutdown(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return SHIM_OK; }
+    for (int d = 0; d < n && d < SHIM_MAX_DEVICES; ++d) {
+        Wavefront& w = g_wf[d];
+        std::lock_guard<std::mutex> lock(w.render_mutex);
+        if (!w.ready && !w.d_out.p && !w.h_out) continue;
+        DeviceGuard g;
+        if (g.enter(d) != cudaSuccess) continue;
+        cudaDeviceSynchronize();
+        w.release();
+    }
+    return SHIM_OK;
+}
+
+SHIM_API uint64_t shim_pool_bytes(int device) {
+    if (device < 0 || device >= SHIM_MAX_DEVICES) return 0;
+    Wavefront& w = g_wf[device];
+    std::lock_guard<std::mutex> lock(w.render_mutex);
+    return (uint64_t)w.pool_bytes();
+}
+
 SHIM_API float* shim_host_alloc(size_t floats) {
     float* p = nullptr;
     if (cudaMallocHost(&p, (floats ? floats : 1) * sizeof(float)) != cudaSuccess) {
@@ -709,17 +948,25 @@ SHIM_API float* shim_host_alloc(size_t floats) {
 SHIM_API void shim_host_free(float* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------------ gate 1
+static int trace_grid(const DeviceScene& ds, int64_t n) {
+    int grid = (int)((n + 255) / 256);
+    int cap = ds.sm_count * 8;
+    return grid > cap ? cap : grid;
+}
+
 SHIM_API int shim_trace_closest_device(shim_scene* s, const float* d_rays, int64_t n, float t_min, float t_max, uint64_t seed,
                                        int32_t* d_prim, float* d_t, void* cuda_stream) {
     NEED(s);
     if (!s->committed) return set_err(SHIM_ERR_STATE, "shim_trace_closest: scene not committed");
     if (n < 0 || (n > 0 && (!d_rays || !d_prim || !d_t))) return set_err(SHIM_ERR_INVALID, "shim_trace_closest: bad arguments");
     if (n == 0) return SHIM_OK;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    int grid = (int)((n + 255) / 256);
-    int cap = s->dev->sm_count * 8;
-    if (grid > cap) grid = cap;
-    trace_closest_kernel<<<grid, 256, 0, st>>>(s->dev->scene.view, d_rays, (long long)n, t_min, t_max, seed, d_prim, d_t, nullptr);
+    int cur_dev = -1;
+    CU(cudaGetDevice(&cur_dev));
+    if (cur_dev != s->dev->primary) return set_err(SHIM_ERR_STATE, "shim_trace_closest: the scene lives on another CUDA device");
+    DeviceScene* ds = nullptr;
+    int rc = scene_on_device(s, cur_dev, &ds);
+    if (rc < 0) return rc;
+    trace_closest_kernel<<<trace_grid(*ds, n), 256, 0, (cudaStream_t)cuda_stream>>>(ds->view, d_rays, (long long)n, t_min, t_max, seed, d_prim, d_t, nullptr);
     CU(cudaGetLastError());
     return SHIM_OK;
 }
@@ -730,8 +977,12 @@ SHIM_API int shim_trace_closest(shim_scene* s, const float* rays, int64_t n, flo
     if (!s->committed) return set_err(SHIM_ERR_STATE, "shim_trace_closest: scene not committed");
     if (n < 0 || (n > 0 && (!rays || !prim || !t))) return set_err(SHIM_ERR_INVALID, "shim_trace_closest: bad arguments");
     if (n == 0) { if (counters) counters[0] = counters[1] = counters[2] = 0; return SHIM_OK; }
+    DeviceGuard guard;
+    CU(guard.enter(s->dev->primary));
+    DeviceScene* ds = nullptr;
+    int rc = scene_on_device(s, s->dev->primary, &ds);
+    if (rc < 0) return rc;
     float* d_rays = nullptr; int32_t* d_prim = nullptr; float* d_t = nullptr; unsigned long long* d_cnt = nullptr;
-    int rc = SHIM_OK;
     auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_prim); cudaFree(d_t); cudaFree(d_cnt); };
 #define CUX(call)                                                                                                     \
     do {                                                                                                              \
@@ -744,10 +995,7 @@ SHIM_API int shim_trace_closest(shim_scene* s, const float* rays, int64_t n, flo
     CUX(cudaMalloc(&d_cnt, 3 * sizeof(unsigned long long)));
     CUX(cudaMemset(d_cnt, 0, 3 * sizeof(unsigned long long)));
     CUX(cudaMemcpy(d_rays, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice));
-    int grid = (int)((n + 255) / 256);
-    int cap = s->dev->sm_count * 8;
-    if (grid > cap) grid = cap;
-    trace_closest_kernel<<<grid, 256>>>(s->dev->scene.view, d_rays, (long long)n, t_min, t_max, seed, d_prim, d_t, counters ? d_cnt : nullptr);
+    trace_closest_kernel<<<trace_grid(*ds, n), 256>>>(ds->view, d_rays, (long long)n, t_min, t_max, seed, d_prim, d_t, counters ? d_cnt : nullptr);
     CUX(cudaGetLastError());
     CUX(cudaMemcpy(prim, d_prim, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     CUX(cudaMemcpy(t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -757,6 +1005,5 @@ SHIM_API int shim_trace_closest(shim_scene* s, const float* rays, int64_t n, flo
         counters[0] = (uint64_t)n; counters[1] = h[1]; counters[2] = h[2];
     }
     cleanup();
-    return rc;
+    return SHIM_OK;
 }
-

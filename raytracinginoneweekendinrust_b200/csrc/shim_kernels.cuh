@@ -52,9 +52,14 @@ struct WfParams {
     f4* ray_o[2];   // origin.xyz, time
     f4* ray_d[2];   // direction.xyz, bounce | sample << 8 (int bits)
     f4* thr[2];     // throughput.rgb, pixel index (int bits)
-    // material queues carry the payload: kind k occupies [k * pool, (k + 1) * pool) of each array
+    // material queues carry the payload.  A set is mq_set_stride entries; two material kinds share one pool-sized
+    // region of it, one growing up from the region's first entry and one down from its last (their counts sum to
+    // at most `pool`), and only the kinds the scene has get a region: entry j of kind k is mq_first[k] + mq_dir[k] * j
     f4* mq_o; f4* mq_d; f4* mq_thr;
     f4* mq_hit;     // t, obj | face << 16, prim_ref, material
+    long long mq_first[MAT_KINDS];
+    int mq_dir[MAT_KINDS];
+    long long mq_set_stride;
     uint32_t* cnt;
     float* accum;   // W*H*3 radiance sums
     const uint32_t* pix_table;
@@ -87,9 +92,11 @@ __device__ __forceinline__ unsigned long long* cnt64(uint32_t* cnt, int slot) {
     return reinterpret_cast<unsigned long long*>(cnt + CNT_U64_BASE) + slot;
 }
 
-// wf_trace pipeline: two material-queue sets (set s: counters mq_counts(p, s), entries from mq_base(p, s, kind))
+// wf_trace pipeline: two material-queue sets (set s: counters mq_counts(p, s), entry j of kind k at mq_slot(p, s, k, j))
 __device__ __forceinline__ uint32_t* mq_counts(const WfParams& p, int set) { return p.cnt + (set ? CNT_MQ1 : CNT_MQ); }
-__device__ __forceinline__ size_t mq_base(const WfParams& p, int set, int kind) { return ((size_t)set * MAT_KINDS + (size_t)kind) * p.pool; }
+__device__ __forceinline__ size_t mq_slot(const WfParams& p, int set, int kind, uint32_t j) {
+    return (size_t)((long long)set * p.mq_set_stride + p.mq_first[kind] + (long long)p.mq_dir[kind] * (long long)j);
+}
 
 // position for this lane in a queue, one atomic per warp; all 32 lanes must call it
 __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred) {
@@ -251,7 +258,7 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
             uint32_t base = 0;
             if ((int)lane == leader) base = atomicAdd(p.cnt + CNT_MQ + kind, (uint32_t)__popc(grp));
             base = __shfl_sync(grp, base, leader);
-            size_t pos = (size_t)kind * p.pool + base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+            size_t pos = mq_slot(p, 0, kind, base + (uint32_t)__popc(grp & ((1u << lane) - 1u)));
             p.mq_o[pos] = o; p.mq_d[pos] = d; p.mq_thr[pos] = t; p.mq_hit[pos] = hv;
         }
     }
@@ -305,40 +312,20 @@ __device__ __forceinline__ SceneView stage_scene(const WfParams& p, unsigned cha
 #ifndef SHIM_EXTEND_THREADS
 #define SHIM_EXTEND_THREADS 640
 #endif
+// threads per block of the specialised kernels (one persistent block per SM; measured in round 1)
+#define SHIM_SOLO_SPHERE_THREADS 896   // sphere-only Bvh worlds: 72 registers
+#define SHIM_SOLO_ANY_THREADS 768      // one plain Bvh of mixed primitives: 80 registers
+#define SHIM_LIST_THREADS 1024         // worlds without a Bvh: 64 registers
+#define SHIM_BVH1_TRI_THREADS 896      // one triangle-only Bvh among rects
 template <bool SMEM, bool COUNT, bool MEDIA, bool HRPP>
 __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
     const WfParams& p = g_p;
     const int cur = (int)p.cnt[CNT_CUR];
     const uint32_t n = p.cnt[cur];
     if (blockIdx.x * blockDim.x >= n) return;  // nothing for this block: do not even stage the scene
-    SceneView sv = p.sv;
-    if (SMEM) {
-        extern __shared__ __align__(128) unsigned char smem[];
-        __shared__ uint64_t bar;
-        if (threadIdx.x == 0) mbar_init(&bar, 1);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const SmemLayout& L = p.smem;
-            mbar_expect_tx(&bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects + L.bytes_sph_mat);
-            if (L.bytes_nodes) bulk_g2s(smem + L.off_nodes, p.sv.nodes, L.bytes_nodes, &bar);
-            if (L.bytes_sph) bulk_g2s(smem + L.off_sph, p.sv.sph, L.bytes_sph, &bar);
-            if (L.bytes_msph) bulk_g2s(smem + L.off_msph, p.sv.msph, L.bytes_msph, &bar);
-            if (L.bytes_rect) bulk_g2s(smem + L.off_rect, p.sv.rect, L.bytes_rect, &bar);
-            if (L.bytes_tri) bulk_g2s(smem + L.off_tri, p.sv.tri, L.bytes_tri, &bar);
-            if (L.bytes_cube) bulk_g2s(smem + L.off_cube, p.sv.cube, L.bytes_cube, &bar);
-            if (L.bytes_objects) bulk_g2s(smem + L.off_objects, p.sv.objects, L.bytes_objects, &bar);
-            if (L.bytes_sph_mat) bulk_g2s(smem + L.off_sph_mat, p.sv.sph_mat, L.bytes_sph_mat, &bar);
-        }
-        sv.nodes = reinterpret_cast<const DevNode*>(smem + p.smem.off_nodes);
-        sv.sph = reinterpret_cast<const double*>(smem + p.smem.off_sph);
-        sv.msph = reinterpret_cast<const f4*>(smem + p.smem.off_msph);
-        sv.rect = reinterpret_cast<const f4*>(smem + p.smem.off_rect);
-        sv.tri = reinterpret_cast<const f4*>(smem + p.smem.off_tri);
-        sv.cube = reinterpret_cast<const f4*>(smem + p.smem.off_cube);
-        sv.objects = reinterpret_cast<const DevObject*>(smem + p.smem.off_objects);
-        sv.sph_mat = reinterpret_cast<const int*>(smem + p.smem.off_sph_mat);
-        mbar_wait(&bar, 0);
-    }
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    const SceneView sv = SMEM ? stage_scene(p, smem, &bar) : p.sv;
     extend_rays<COUNT, MEDIA, HRPP>(p, sv, cur, n);
 }
 
@@ -408,7 +395,7 @@ __device__ __forceinline__ void bvh1_finish(const WfParams& p, const SceneView& 
         uint32_t base = 0;
         if ((int)lane == leader) base = atomicAdd(p.cnt + CNT_MQ + kind, (uint32_t)__popc(grp));
         base = __shfl_sync(grp, base, leader);
-        size_t pos = (size_t)kind * p.pool + base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+        size_t pos = mq_slot(p, 0, kind, base + (uint32_t)__popc(grp & ((1u << lane) - 1u)));
         p.mq_o[pos] = p.ray_o[cur][i]; p.mq_d[pos] = p.ray_d[cur][i]; p.mq_thr[pos] = p.thr[cur][i]; p.mq_hit[pos] = hv;
     }
 }
@@ -541,33 +528,8 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_bvh1() {
     const uint32_t n = p.cnt[cur];
     if (blockIdx.x * blockDim.x * SHIM_BVH1_GROUP >= n) return;
     extern __shared__ __align__(128) unsigned char smem[];   // [scene image (SMEM)] [per-warp entry lists]
-    SceneView sv = p.sv;
-    if (SMEM) {
-        __shared__ uint64_t bar;
-        if (threadIdx.x == 0) mbar_init(&bar, 1);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const SmemLayout& L = p.smem;
-            mbar_expect_tx(&bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects + L.bytes_sph_mat);
-            if (L.bytes_nodes) bulk_g2s(smem + L.off_nodes, p.sv.nodes, L.bytes_nodes, &bar);
-            if (L.bytes_sph) bulk_g2s(smem + L.off_sph, p.sv.sph, L.bytes_sph, &bar);
-            if (L.bytes_msph) bulk_g2s(smem + L.off_msph, p.sv.msph, L.bytes_msph, &bar);
-            if (L.bytes_rect) bulk_g2s(smem + L.off_rect, p.sv.rect, L.bytes_rect, &bar);
-            if (L.bytes_tri) bulk_g2s(smem + L.off_tri, p.sv.tri, L.bytes_tri, &bar);
-            if (L.bytes_cube) bulk_g2s(smem + L.off_cube, p.sv.cube, L.bytes_cube, &bar);
-            if (L.bytes_objects) bulk_g2s(smem + L.off_objects, p.sv.objects, L.bytes_objects, &bar);
-            if (L.bytes_sph_mat) bulk_g2s(smem + L.off_sph_mat, p.sv.sph_mat, L.bytes_sph_mat, &bar);
-        }
-        sv.nodes = reinterpret_cast<const DevNode*>(smem + p.smem.off_nodes);
-        sv.sph = reinterpret_cast<const double*>(smem + p.smem.off_sph);
-        sv.msph = reinterpret_cast<const f4*>(smem + p.smem.off_msph);
-        sv.rect = reinterpret_cast<const f4*>(smem + p.smem.off_rect);
-        sv.tri = reinterpret_cast<const f4*>(smem + p.smem.off_tri);
-        sv.cube = reinterpret_cast<const f4*>(smem + p.smem.off_cube);
-        sv.objects = reinterpret_cast<const DevObject*>(smem + p.smem.off_objects);
-        sv.sph_mat = reinterpret_cast<const int*>(smem + p.smem.off_sph_mat);
-        mbar_wait(&bar, 0);
-    }
+    __shared__ uint64_t bar;
+    const SceneView sv = SMEM ? stage_scene(p, smem, &bar) : p.sv;
     extend_rays_bvh1<COUNT, ONLY>(p, sv, cur, n, reinterpret_cast<Bvh1Entry*>(smem + (SMEM ? p.smem.total : 0u)));
 }
 #define SHIM_BVH1_SMEM_BYTES_T(T) (((T) / 32) * SHIM_BVH1_GROUP * 32 * (int)sizeof(Bvh1Entry))
@@ -608,7 +570,7 @@ __device__ __forceinline__ void shade_chunk(const WfParams& p, int cur, uint32_t
     so.cont = false; so.ray.o = mk3(0, 0, 0); so.ray.d = mk3(0, 0, 0); so.ray.time = 0; so.thr = mk3(0, 0, 0);
     uint32_t bs = 0, pixel = 0;
     if (j < n) {
-        size_t q = (size_t)KIND * p.pool + j;
+        size_t q = mq_slot(p, 0, KIND, j);
         f4 o = p.mq_o[q], d = p.mq_d[q], t = p.mq_thr[q], hv = p.mq_hit[q];
         Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
         bs = (uint32_t)f2i(d.w); pixel = (uint32_t)f2i(t.w);
@@ -760,7 +722,7 @@ __global__ void __launch_bounds__(128) wf_tail() {
 // 64-byte read and one 64-byte write instead of 224 bytes through two queues, and two launches less per iteration.
 template <int KIND>
 __device__ __noinline__ bool trace_shade_entry(const WfParams& p, int set, uint32_t j, f4& o, f4& d, f4& t) {
-    const size_t q = mq_base(p, set, KIND) + j;
+    const size_t q = mq_slot(p, set, KIND, j);
     const f4 eo = p.mq_o[q], ed = p.mq_d[q], et = p.mq_thr[q], hv = p.mq_hit[q];
     Ray r; r.o = mk3(eo.x, eo.y, eo.z); r.d = mk3(ed.x, ed.y, ed.z); r.time = eo.w;
     const uint32_t bs = (uint32_t)f2i(ed.w), pixel = (uint32_t)f2i(et.w);
@@ -834,7 +796,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_trace_solo() {
             uint32_t base = 0;
             if ((int)lane == leader) base = atomicAdd(out_cnt + kind, (uint32_t)__popc(grp));
             base = __shfl_sync(grp, base, leader);
-            const size_t pos = mq_base(p, 1 - cur, kind) + base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+            const size_t pos = mq_slot(p, 1 - cur, kind, base + (uint32_t)__popc(grp & ((1u << lane) - 1u)));
             p.mq_o[pos] = o; p.mq_d[pos] = d; p.mq_thr[pos] = t; p.mq_hit[pos] = hv;
         }
     }
@@ -846,13 +808,23 @@ __global__ void __launch_bounds__(THREADS, 1) wf_trace_solo() {
 template <int ONLY>
 __global__ void __launch_bounds__(128) wf_tail_mq() {
     const WfParams& p = g_p;
-    const int nxt = 1 - (int)p.cnt[CNT_CUR];
+    // Thread 0 reads the counters once and the block branches on that copy: the last block to take a ticket rewrites
+    // them (next iteration), so no thread may look at global memory again after its block's ticket is taken.
+    __shared__ uint32_t s_seg[MAT_KINDS + 2];
+    if (threadIdx.x == 0) {
+        const int nx = 1 - (int)p.cnt[CNT_CUR];
+#pragma unroll
+        for (int k = 0; k < MAT_KINDS; ++k) s_seg[k] = mq_counts(p, nx)[k];
+        s_seg[MAT_KINDS] = (*cnt64(p.cnt, C64_NEXT_SAMPLE) >= p.total_samples) ? 1u : 0u;
+        s_seg[MAT_KINDS + 1] = (uint32_t)nx;
+    }
+    __syncthreads();
+    const int nxt = (int)s_seg[MAT_KINDS + 1];
     uint32_t seg_n[MAT_KINDS], n = 0;
 #pragma unroll
-    for (int k = 0; k < MAT_KINDS; ++k) { seg_n[k] = mq_counts(p, nxt)[k]; n += seg_n[k]; }
-    const bool all_started = *cnt64(p.cnt, C64_NEXT_SAMPLE) >= p.total_samples;
+    for (int k = 0; k < MAT_KINDS; ++k) { seg_n[k] = s_seg[k]; n += seg_n[k]; }
+    const bool all_started = s_seg[MAT_KINDS] != 0u;
     if (n == 0 || n > p.tail_threshold || !all_started) {
-        // the counters may only change once every block has read them: the last block to get here ends the iteration
         if (threadIdx.x == 0) {
             const uint32_t ticket = atomicAdd(p.cnt + CNT_TICKET, 1u);
             if (ticket == gridDim.x - 1) {
@@ -870,7 +842,7 @@ __global__ void __launch_bounds__(128) wf_tail_mq() {
         int kind = 0;
         uint32_t j = i;
         while (j >= seg_n[kind]) { j -= seg_n[kind]; ++kind; }
-        const size_t q = mq_base(p, nxt, kind) + j;
+        const size_t q = mq_slot(p, nxt, kind, j);
         const f4 eo = p.mq_o[q], ed = p.mq_d[q], et = p.mq_thr[q], hv = p.mq_hit[q];
         Ray r; r.o = mk3(eo.x, eo.y, eo.z); r.d = mk3(ed.x, ed.y, ed.z); r.time = eo.w;
         const uint32_t sample = (uint32_t)f2i(ed.w) >> 8, pixel = (uint32_t)f2i(et.w);

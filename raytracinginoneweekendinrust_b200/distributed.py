@@ -27,7 +27,9 @@ def shard_params(make_params, total_spp: int, rank: int, world: int, mode: str =
     flags = kw.pop("flags", 0) | capi.RENDER_RAW_SUM
     if mode == "samples":
         begin, count = shard_samples(total_spp, rank, world)
-        return make_params(spp=total_spp, sample_begin=begin, sample_count=count, flags=flags, **kw), count
+        # world > total_spp leaves some ranks without samples: sample_count 0 would mean "all of them" to the C ABI
+        # (shimmer_b200.h), -1 is its explicit "none" (the rank still takes part in the reduce with a zero framebuffer)
+        return make_params(spp=total_spp, sample_begin=begin, sample_count=count if count > 0 else -1, flags=flags, **kw), count
     if mode == "tiles":
         return make_params(spp=total_spp, tile_rank=rank, tile_world=world, flags=flags, **kw), total_spp
     raise ValueError("mode must be 'samples' or 'tiles'")

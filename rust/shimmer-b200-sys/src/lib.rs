@@ -25,6 +25,9 @@ pub const SHIM_RENDER_PREDICTORS: i32 = 2;
 pub const SHIM_RENDER_COUNT_NODES: i32 = 4;
 pub const SHIM_RENDER_PROFILE: i32 = 8;
 
+pub const SHIM_SHARD_SAMPLES: c_int = 0;
+pub const SHIM_SHARD_TILES: c_int = 1;
+
 /// The nine `Camera::new` arguments (camera.rs:44-54).
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
@@ -78,6 +81,10 @@ pub struct shim_stats {
     pub generate_ms: f64,
     pub extend_launches: u64,
     pub extend_variant: u64,
+    pub pool_paths: u64,
+    pub pool_bytes: u64,
+    pub devices: u64,
+    pub wall_ms: f64,
 }
 
 extern "C" {
@@ -136,6 +143,13 @@ extern "C" {
         s: *mut shim_scene, cam: *const shim_camera, p: *const shim_render_params, d_out_rgb: *mut f32,
         stats: *mut shim_stats, cuda_stream: *mut c_void,
     ) -> c_int;
+
+    pub fn shim_render_multi(
+        s: *mut shim_scene, cam: *const shim_camera, p: *const shim_render_params, n_devices: c_int, devices: *const c_int,
+        mode: c_int, out_rgb: *mut f32, stats: *mut shim_stats,
+    ) -> c_int;
+    pub fn shim_shutdown() -> c_int;
+    pub fn shim_pool_bytes(device: c_int) -> u64;
 
     pub fn shim_trace_closest(
         s: *mut shim_scene, rays: *const f32, n: i64, t_min: f32, t_max: f32, seed: u64,

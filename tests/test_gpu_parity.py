@@ -137,9 +137,9 @@ def test_kernel_variants_agree():
     p = api.make_params(192, 128, 6, 50, background=info.background, seed=5)
     ref, st = g.render(cam, p)
     assert st.extend_variant == 4                  # one plain Bvh of spheres -> the wf_trace pipeline
-    for env in ({"SHIM_NO_GRAPH": "1"}, {"SHIM_TRACE_T": "640", "SHIM_SOLO_ANY": "1"}, {"SHIM_TAIL": "0"},
+    for env in ({"SHIM_NO_GRAPH": "1"}, {"SHIM_SOLO_ANY": "1"}, {"SHIM_TAIL": "0"},
                 {"SHIM_NO_TRACE": "1"}, {"SHIM_NO_TRACE": "1", "SHIM_NO_FUSE": "1"}, {"SHIM_SOLO": "0"},
-                {"SHIM_NO_TRACE": "1", "SHIM_SOLO": "768", "SHIM_SOLO_ANY": "1"}, {"SHIM_NO_TRACE": "1", "SHIM_TAIL": "0"},
+                {"SHIM_NO_TRACE": "1", "SHIM_SOLO_ANY": "1"}, {"SHIM_NO_TRACE": "1", "SHIM_TAIL": "0"},
                 {"SHIM_SOLO": "0", "SHIM_NO_GRAPH": "1", "SHIM_TAIL": "0"}):
         img, st2 = _render_with_env(g, cam, p, env)
         assert st2.rays == st.rays, env

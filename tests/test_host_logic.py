@@ -85,3 +85,20 @@ def test_sample_shards_partition_the_range():
         assert got == list(range(total))
     with pytest.raises(ValueError):
         distributed.shard_samples(10, 2, 2)
+
+
+def test_ranks_without_samples_ask_for_none_not_all():
+    """world > total_spp: the C ABI reads sample_count 0 as "every sample" (shimmer_b200.h), so a rank whose range is
+    empty must pass the explicit -1 (spp 4 on 8 GPUs rendered 20 samples / 4)."""
+    from raytracinginoneweekendinrust_b200 import api
+    total, world = 4, 8
+    rendered = 0
+    for r in range(world):
+        p, count = distributed.shard_params(api.make_params, total, r, world, width=8, height=8)
+        assert p.samples_per_pixel == total
+        if count == 0:
+            assert p.sample_count == -1
+        else:
+            assert p.sample_count == count and p.sample_begin == rendered
+        rendered += count
+    assert rendered == total
