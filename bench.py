@@ -8,9 +8,17 @@ traversal + intersection and scatter/shade, i.e. everything under Renderer::rend
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config C1] [--impl reference]
 
-N > 1 (launched by torch.distributed.run): sample-range sharding, weak scaling — every rank
-renders `spp` samples per pixel of its own absolute sample range over the full image, then one
-framebuffer reduce over NCCL; no collective inside the wavefront loop.
+The one JSON line carries, next to the headline (`value`, C1 device-timed):
+  parity    the framebuffer of the TIMED configuration against the CPU oracle on the same Philox stream
+  roofline  the dominant kernel against its binding ceiling (instruction issue) with the HBM fraction beside it
+  configs   BASELINE.json's other configurations (C2..C5 and their variants) at a bounded sample count each:
+            Mrays/s, samples/s, end to end, roofline, the CPU arm timed beside it
+  strong    (N > 1) ONE fixed image sharded over the N ranks, one NCCL reduce, against rank 0 rendering it alone
+
+N > 1 (launched by torch.distributed.run): sample-range sharding.  `value` is weak scaling — every rank
+renders `spp_per_gpu` samples per pixel of its own absolute sample range over the full image (the image
+then has N x spp_per_gpu samples; `config.spp` says so), one framebuffer reduce over NCCL at the end; no
+collective inside the wavefront loop.
 """
 from __future__ import annotations
 
@@ -143,24 +151,43 @@ def workload(args):
     return cfg, W, H, spp
 
 
-def scene_kwargs(cfg, args):
+def scene_kwargs(cfg, args, extra=None):
     kw = dict(cfg.scene_kwargs)
+    if extra:
+        kw.update(extra)
     if args.tris > 0 and cfg.scene in ("bunny", "gargoyle", "igea-hrpp"):
         kw["n_tris"] = args.tris
     return kw
 
 
-def config_dict(cfg, W, H, spp, args, extra=None):
-    d = {"workload": f"{cfg.key} {cfg.scene} {W}x{H} {spp}spp depth{cfg.max_depth}", "scene": cfg.scene, "width": W, "height": H,
-         "spp": spp, "max_depth": cfg.max_depth, "scene_seed": 1, "tile": "8x8",
-         "l2": "256 MiB buffer written between timed steps (L2 flush)"}
-    if extra:
-        d.update(extra)
-    return d
+def config_dict(cfg, W, H, spp_per_gpu, n_gpus):
+    """Only what names the workload (identical in both arms): under weak scaling every GPU renders spp_per_gpu samples
+    per pixel of its own sample range, so the image has n_gpus x spp_per_gpu samples."""
+    return {"workload": f"{cfg.key} {cfg.scene} {W}x{H} {spp_per_gpu}spp depth{cfg.max_depth}", "scene": cfg.scene, "width": W, "height": H,
+            "spp": spp_per_gpu * n_gpus, "spp_per_gpu": spp_per_gpu, "max_depth": cfg.max_depth, "scene_seed": 1, "tile": "8x8",
+            "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+
+
+# BASELINE.json's other configurations and their variants: (label, config key, scene kwargs, time the CPU arm too)
+EXTRA = [
+    ("C2", "C2", {}, True),
+    ("C3", "C3", {"material": "lambertian"}, True),
+    ("C3-dielectric", "C3", {"material": "dielectric"}, False),
+    ("C3-metal", "C3", {"material": "metal"}, False),
+    ("C4", "C4", {"predictors": False}, True),
+    ("C4-hrpp", "C4", {"predictors": True}, False),
+    ("C5", "C5", {"predictor": False}, True),
+    ("C5-hrpp", "C5", {"predictor": True}, True),
+]
+# SURVEY.md §8d instruction budget: 30 per box test (60 per 64-byte node = both child boxes), per primitive test by
+# the scene's dominant primitive (f64 sphere 2 x 45, triangle 45, Cornell's rect / six-rect cube / medium mix 60),
+# 150 for shading when the dominant kernel shades too (wf_trace_solo)
+PRIM_BUDGET = {"random-spheres": 90, "cornell-smoke": 60, "bunny": 45, "igea-hrpp": 45, "gargoyle": 45, "showcase": 90}
+PRIM_BYTES = {"random-spheres": 32, "cornell-smoke": 32, "showcase": 32}
 
 
 # -------------------------------------------------------------------------------------------- CPU arm
-def run_cpu(args, steps, warmup, budget_s, threads=0):
+def run_cpu(cfg, W, H, spp, kw, steps, warmup, budget_s, threads=0):
     """The reference's path on the host cores: the C++ restatement in oracle/ in reference mode
     (recursive both-children traversal, per-node divides, f64 spheres, recursion, 8x8 tiles pulled by
     one thread per logical core), xorshift RNG standing in for thread_rng.  Each step renders a bounded
@@ -169,9 +196,15 @@ def run_cpu(args, steps, warmup, budget_s, threads=0):
     sys.path.insert(0, str(ROOT / "tests"))
     import support
     from raytracinginoneweekendinrust_b200 import scenes
-    cfg, W, H, spp = workload(args)
     o = support.OracleScene()
-    info = scenes.build(o, cfg.scene, seed=1, **scene_kwargs(cfg, args))
+    info = scenes.build(o, cfg.scene, seed=1, **kw)
+
+    # bounded sample: configurations above half a megapixel are timed on a window-preserving reduced image (same camera,
+    # same scene, W/k x H/k pixels; rays per sample and the per-ray cost do not depend on the pixel count)
+    k = 1
+    while (W // k) * (H // k) > 600_000:
+        k += 1
+    W, H = W // k, H // k
 
     def params(n_spp):
         return o.params(W, H, n_spp, cfg.max_depth, background=info.background, seed=0, rng_fast=True, iterative=False,
@@ -187,10 +220,16 @@ def run_cpu(args, steps, warmup, budget_s, threads=0):
             times.append(st.seconds)
             best = st
     sec = float(np.mean(times))
+    o.close()
     return {"mrays": best.rays / sec / 1e6, "samples_per_s": best.samples / sec, "seconds": sec, "threads": int(best.threads),
             "rays": int(best.rays), "sample": f"{cfg.scene} {W}x{H} at {cpu_spp} spp (of {spp}), depth {cfg.max_depth}, "
-                                              f"{steps} timed render(s) after {warmup} warm-up",
+                                              f"{steps} timed render(s) after {warmup} warm-up" + (", predictors on" if info.predictors else ""),
             "nodes_per_ray": best.node_visits / max(1, best.rays), "prims_per_ray": best.prim_tests / max(1, best.rays)}
+
+
+def cpu_entry(c):
+    return {"value": c["mrays"], "unit": "Mrays/s", "cores": c["threads"], "kind": "port", "sample": c["sample"],
+            "samples_per_s": c["samples_per_s"], "ref_nodes_per_ray": c["nodes_per_ray"], "ref_prims_per_ray": c["prims_per_ray"]}
 
 
 def main_reference(args):
@@ -199,11 +238,11 @@ def main_reference(args):
         return
     result_out = _claim_stdout()
     cfg, W, H, spp = workload(args)
-    r = run_cpu(args, args.steps, args.warmup, budget_s=120.0)
+    r = run_cpu(cfg, W, H, spp, scene_kwargs(cfg, args), args.steps, args.warmup, budget_s=120.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["mrays"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (+f64 sphere quadratic)", "data": "synthetic",
-            "config": config_dict(cfg, W, H, spp, args),
+            "config": config_dict(cfg, W, H, spp, args.gpus),
             "samples_per_s": r["samples_per_s"],
             "cpu_baseline": {"value": r["mrays"], "unit": "Mrays/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -219,6 +258,130 @@ def _claim_stdout():
     real = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     return real
+
+
+def load_ncu():
+    """ncu figures per config (thread instructions per ray, active lanes, issue utilisation, DRAM bytes) measured once
+    per kernel change under gpurun and committed under profiles/ (tools/ncu_summary.py writes the file)."""
+    p = ROOT / "profiles" / "r02_ncu.json"
+    return json.loads(p.read_text()) if p.exists() else {}
+
+
+def roofline_entry(scene_name, kernel, fused, st_cnt, prof_stats, clocks, ncu):
+    """Roofline of the dominant (closest-hit) kernel from the event-timed profile pass: the binding ceiling is
+    instruction issue, HBM is reported beside it."""
+    peak_hbm, peak_src, sm_max = load_peaks()
+    nodes_per_ray = st_cnt.node_visits / max(1, st_cnt.rays)
+    prims_per_ray = st_cnt.prim_tests / max(1, st_cnt.rays)
+    ext_ms = sum(s.extend_ms for s in prof_stats)
+    ext_launch = sum(s.extend_launches for s in prof_stats)
+    rays = sum(s.rays for s in prof_stats)
+    prof_ms = sum(s.device_ms for s in prof_stats)
+    if ext_ms <= 0 or rays <= 0:
+        return None
+    hbm_bytes_per_ray = 128.0   # SURVEY §8d B_state: the ray record in, ray + hit record out, amortised accumulate traffic
+    onchip_bytes_per_ray = nodes_per_ray * 64 + prims_per_ray * PRIM_BYTES.get(scene_name, 48)
+    sm_clk = (clocks.get("sm_mhz") or sm_max) * 1e6
+    budget = nodes_per_ray * 2 * 30 + prims_per_ray * PRIM_BUDGET.get(scene_name, 45) + (150 if fused else 0)
+    issue_peak = 148 * 128 * sm_clk / budget / 1e6          # Mrays/s at 32 of 32 lanes and every issue slot used
+    achieved = rays / (ext_ms / 1e3) / 1e6                   # Mrays/s inside the kernel
+    hbm_achieved = hbm_bytes_per_ray * rays / (ext_ms / 1e3) / 1e9
+    r = {"bound": "issue", "kernel": kernel, "achieved": achieved, "peak": issue_peak, "unit": "Mrays/s", "frac": achieved / issue_peak,
+         "peak_definition": "148 SMs x 4 schedulers x 32 lanes x SM clock / budgeted instructions per ray (SURVEY.md §8d: 60 per node, "
+                            f"{PRIM_BUDGET.get(scene_name, 45)} per primitive test" + (", 150 shading" if fused else "") + ")",
+         "budget_inst_per_ray": budget, "sm_mhz": sm_clk / 1e6, "nodes_per_ray": nodes_per_ray, "prims_per_ray": prims_per_ray,
+         "kernel_ms_per_step": ext_ms / max(1, len(prof_stats)), "kernel_share_of_step": ext_ms / prof_ms if prof_ms else None,
+         "kernel_launches_per_step": ext_launch / max(1, len(prof_stats)),
+         "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": peak_hbm, "frac": hbm_achieved / peak_hbm, "peak_source": peak_src,
+                 "algorithmic_bytes_per_ray": hbm_bytes_per_ray, "algorithmic_bytes_per_step": hbm_bytes_per_ray * rays / max(1, len(prof_stats))},
+         "onchip": {"bytes_per_ray": onchip_bytes_per_ray, "achieved_gbs": onchip_bytes_per_ray * rays / (ext_ms / 1e3) / 1e9,
+                    "level": "shared memory (TMA-staged scene image)" if fused or scene_name in ("cornell-smoke",) else "L1/L2"},
+         "measured_on": f"{len(prof_stats)} extra step(s) of the same workload right after the timed ones, CUDA events around every launch "
+                        "of the kernel on its stream (timed steps carry no per-kernel events)"}
+    n = ncu.get(kernel)
+    r["traffic"] = None
+    if n:
+        # like for like: DRAM bytes and algorithmic bytes of the SAME captured launches
+        r["traffic"] = n.get("dram_bytes_per_launch")
+        r["ncu"] = n
+        if n.get("thread_inst_per_ray"):
+            r["measured_inst_per_ray"] = n["thread_inst_per_ray"]
+            r["frac_vs_measured_inst"] = achieved / (148 * 128 * sm_clk / n["thread_inst_per_ray"] / 1e6)
+    return r
+
+
+def measure_extra(label, key, kw, with_cpu, args, api, capi, scenes, torch, dev, stream, flush, clocks, ncu):
+    """One of BASELINE.json's other configurations at a bounded sample count: device-timed steps, end to end through
+    the host-buffer C ABI call, roofline of its closest-hit kernel, CPU arm beside it."""
+    cfg = scenes.configs()[key]
+    W, H = cfg.width, cfg.height
+    spp = int(max(1, min(cfg.spp, args.extra_samples // (W * H))))
+    kwargs = scene_kwargs(cfg, args, kw)
+    t0 = time.perf_counter()
+    scene = api.Scene()
+    info = scenes.build(scene, cfg.scene, seed=1, **kwargs)
+    build_s = time.perf_counter() - t0
+    base = capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0)
+    p = api.make_params(W, H, spp, cfg.max_depth, background=info.background, seed=0, flags=base)
+    fb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    for _ in range(2):
+        scene.render_device(cfg.camera, p, fb.data_ptr(), stream.cuda_stream)
+        flush.zero_()
+    ev, stats = [], []
+    for _ in range(args.extra_steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        stats.append(scene.render_device(cfg.camera, p, fb.data_ptr(), stream.cuda_stream))
+        b.record(stream)
+        flush.zero_()
+        ev.append((a, b))
+    torch.cuda.synchronize(dev)
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    rays = sum(s.rays for s in stats)
+    out = {"workload": f"{key} {cfg.scene} {W}x{H} {spp}spp (of {cfg.spp}) depth{cfg.max_depth}", "scene_args": kwargs, "notes": info.notes,
+           "value": rays / ms / 1e3, "unit": "Mrays/s", "samples_per_s": sum(s.samples for s in stats) / (ms / 1e3),
+           "ms_per_step": ms / len(ev), "steps": len(ev), "rays_per_sample": rays / max(1, sum(s.samples for s in stats)),
+           "iterations_per_step": stats[-1].iterations, "gpu_launches_per_step": int(stats[-1].kernel_launches),
+           "scene_device_bytes": scene.device_bytes(), "pool_bytes": int(stats[-1].pool_bytes), "host_scene_build_s": build_s}
+    kernel = capi.Stats.EXTEND_KERNELS.get(int(stats[-1].extend_variant), "wf_extend")
+    if info.predictors:
+        st = stats[-1]
+        tot = st.hrpp_true_positive + st.hrpp_false_positive + st.hrpp_no_prediction
+        out["hrpp"] = {"true_positive": st.hrpp_true_positive / max(1, tot), "false_positive": st.hrpp_false_positive / max(1, tot),
+                       "no_prediction": st.hrpp_no_prediction / max(1, tot), "lookups": int(tot),
+                       "note": "predictions return the first hit found in a predicted leaf (bvh.rs:145-156): the image is approximate by design"}
+        kernel = "wf_extend<HRPP>"
+    # roofline: node / primitive counters from a 1-spp counting render (predictor off: the counters need the plain walk)
+    if not info.predictors:
+        pc = api.make_params(W, H, 1, cfg.max_depth, background=info.background, seed=0, flags=capi.RENDER_RAW_SUM | capi.RENDER_COUNT_NODES)
+        st_cnt = scene.render_device(cfg.camera, pc, fb.data_ptr(), stream.cuda_stream)
+        pp = api.make_params(W, H, spp, cfg.max_depth, background=info.background, seed=0, flags=base | capi.RENDER_PROFILE)
+        flush.zero_()
+        prof = [scene.render_device(cfg.camera, pp, fb.data_ptr(), stream.cuda_stream)]
+        out["roofline"] = roofline_entry(cfg.scene, kernel, int(stats[-1].extend_variant) == 4, st_cnt, prof, clocks, ncu.get(label, {}))
+    # end to end: commit + render into a page-locked host framebuffer
+    hfb = api.HostFramebuffer(H, W)
+    e2e = []
+    for k in range(3):
+        s2 = api.Scene()
+        scenes.SCENES[cfg.scene](s2, seed=1, **kwargs)       # host-side recording (untimed, like Bvh::new in the reference)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        s2.commit()
+        _, st2 = s2.render(cfg.camera, api.make_params(W, H, spp, cfg.max_depth, background=info.background, seed=0, flags=base), out=hfb.array)
+        dt = time.perf_counter() - t0
+        if k > 0:
+            e2e.append((dt, st2.rays))
+        s2.close()
+    hfb.close()
+    out["e2e"] = {"value": sum(r for _, r in e2e) / sum(t for t, _ in e2e) / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * sum(t for t, _ in e2e) / len(e2e),
+                  "h2d_bytes_per_step": scene.device_bytes(), "d2h_bytes_per_step": W * H * 12}
+    scene.close()
+    del fb
+    if with_cpu and not args.no_cpu:
+        out["cpu_baseline"] = cpu_entry(run_cpu(cfg, W, H, spp, kwargs, 1, 0, budget_s=args.extra_cpu_s))
+        out["speedup_vs_cpu"] = {"device": out["value"] / out["cpu_baseline"]["value"], "e2e": out["e2e"]["value"] / out["cpu_baseline"]["value"]}
+    return out
 
 
 def main_gpu(args):
@@ -238,25 +401,25 @@ def main_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, W, H, spp = workload(args)
+    kwargs = scene_kwargs(cfg, args)
     scene = api.Scene()
-    info = scenes.build(scene, cfg.scene, seed=1, **scene_kwargs(cfg, args))
+    info = scenes.build(scene, cfg.scene, seed=1, **kwargs)
     base_flags = capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0)
-    flags = base_flags  # timed steps carry no per-kernel events: recording them costs ~10 % of a step
     total_spp = spp * world
     # weak scaling: rank r renders absolute samples [r*spp, (r+1)*spp) of a total_spp-sample image
     assert distributed.shard_samples(total_spp, rank, world) == (rank * spp, spp)
     params = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
-                             sample_count=spp, flags=flags, pool_paths=args.pool)
+                             sample_count=spp, flags=base_flags, pool_paths=args.pool)   # no per-kernel events in timed steps (~10 % of a step)
+    prof_params = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
+                                  sample_count=spp, flags=base_flags | capi.RENDER_PROFILE, pool_paths=args.pool)
     fb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
-    prof_params = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
-                                  sample_count=spp, flags=base_flags | capi.RENDER_PROFILE, pool_paths=args.pool)
-
     def step(prm=None):
         st = scene.render_device(cfg.camera, prm or params, fb.data_ptr(), stream.cuda_stream)
-        distributed.reduce_framebuffer(fb, total_spp, dst=0) if world > 1 else None  # one framebuffer sum over NVLink
+        if world > 1:
+            dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)   # the one framebuffer sum over NVLink
         return st
 
     def barrier():
@@ -278,10 +441,12 @@ def main_gpu(args):
         ev[k][0].record(stream)
         stats.append(step())
         ev[k][1].record(stream)
+        if k == args.steps - 1:
+            image_sum = fb.clone()   # the timed configuration's own framebuffer (raw sums; on rank 0 the reduced ones), for the parity check
         flush.zero_()  # L2 flush between timed steps (outside the event pair)
     barrier()
     wall = time.perf_counter() - wall0
-    # roofline pass: the same step again with CUDA events around every wf_extend launch (on its stream)
+    # roofline pass: the same step again with CUDA events around every launch of the closest-hit kernel (on its stream)
     prof_stats = []
     for _ in range(args.profile_steps):
         flush.zero_()
@@ -300,24 +465,29 @@ def main_gpu(args):
     value = float(rays.item()) / tot_s / 1e6
     samples_per_s = float(samples.item()) / tot_s
 
-    # ---- e2e: the C-ABI call with HOST buffers: commit (flatten + H2D of the scene) + render + D2H framebuffer
+    # ---- e2e: the C-ABI call with HOST buffers.  One rank: shim_commit (flatten + scene H2D) + shim_render into a page-locked
+    # host framebuffer (D2H).  N ranks: commit + render of the rank's shard + the NCCL framebuffer sum + rank 0's D2H of the image.
     e2e_ms, h2d, d2h = [], 0, W * H * 3 * 4
     e2e_rays = 0
-    p_e2e = api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, sample_begin=rank * spp,
-                            sample_count=spp, flags=capi.RENDER_RAW_SUM | (capi.RENDER_PREDICTORS if info.predictors else 0),
-                            pool_paths=args.pool)
     E2E_WARM = 4
-    # the caller-owned host framebuffer, reused like a renderer would: page-locked (shim_host_alloc) unless --pageable-fb
     pinned_fb = None if args.pageable_fb else api.HostFramebuffer(H, W)
     host_fb = np.zeros((H, W, 3), np.float32) if pinned_fb is None else pinned_fb.array
+    host_t = torch.from_numpy(host_fb) if world > 1 else None
     for k in range(args.e2e_steps + E2E_WARM if args.e2e_steps > 0 else 0):
         s2 = api.Scene()
-        scenes.SCENES[cfg.scene](s2, seed=1, **scene_kwargs(cfg, args))  # host-side recording (untimed)
+        scenes.SCENES[cfg.scene](s2, seed=1, **kwargs)  # host-side recording (untimed: Bvh::new is outside render in the reference too)
         barrier()
         t0 = time.perf_counter()
         s2.commit()
         tc = time.perf_counter()
-        _, st2 = s2.render(cfg.camera, p_e2e, out=host_fb)
+        if world == 1:
+            _, st2 = s2.render(cfg.camera, params, out=host_fb)
+        else:
+            st2 = s2.render_device(cfg.camera, params, fb.data_ptr(), stream.cuda_stream)
+            dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                host_t.copy_(fb, non_blocking=True)
+            torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if os.environ.get("BENCH_DEBUG"):
             print(f"e2e step {k}: commit {1e3 * (tc - t0):.2f} ms, render {1e3 * (time.perf_counter() - tc):.2f} ms "
@@ -334,73 +504,109 @@ def main_gpu(args):
         dist.all_reduce(e2e_r, op=dist.ReduceOp.SUM)
     e2e_value = float(e2e_r.item()) / (float(e2e_t.item()) / 1e3) / 1e6 if e2e_ms else None
 
+    # ---- strong scaling (N > 1): ONE fixed image (strong_spp samples per pixel) sharded over the ranks by sample range,
+    # one NCCL reduce; against rank 0 rendering the whole image alone.  Device-timed, max over ranks.
+    strong = None
+    if world > 1:
+        S = args.strong_spp
+        b, c = distributed.shard_samples(S, rank, world)
+        ps = api.make_params(W, H, S, cfg.max_depth, background=info.background, seed=0, sample_begin=b, sample_count=c if c > 0 else -1,
+                             flags=base_flags, pool_paths=args.pool)
+        p1 = api.make_params(W, H, S, cfg.max_depth, background=info.background, seed=0, flags=base_flags, pool_paths=args.pool)
+        for _ in range(2):
+            step(ps)
+        barrier()
+        sev = []
+        for _ in range(args.strong_steps):
+            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); step(ps); bb.record(stream)
+            flush.zero_()
+            sev.append((a, bb))
+        barrier()
+        tN = torch.tensor([sum(a.elapsed_time(bb) for a, bb in sev) / len(sev)], dtype=torch.float64, device=dev)
+        render_only = torch.tensor([0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tN, op=dist.ReduceOp.MAX)
+        t1 = torch.tensor([0.0], dtype=torch.float64, device=dev)
+        if rank == 0:   # the same image on one GPU (no reduce), the other ranks wait
+            scene.render_device(cfg.camera, p1, fb.data_ptr(), stream.cuda_stream)
+            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            st1 = scene.render_device(cfg.camera, p1, fb.data_ptr(), stream.cuda_stream)
+            bb.record(stream)
+            torch.cuda.synchronize(dev)
+            t1[0] = a.elapsed_time(bb)
+            render_only[0] = st1.rays
+        barrier()
+        if rank == 0:
+            strong = {"workload": f"{cfg.key} {cfg.scene} {W}x{H} {S}spp depth{cfg.max_depth}: ONE image, sample ranges over {world} ranks, one NCCL reduce",
+                      "ms_1gpu": float(t1.item()), f"ms_{world}gpu": float(tN.item()), "speedup": float(t1.item()) / float(tN.item()),
+                      "efficiency": float(t1.item()) / float(tN.item()) / world, "value": float(render_only.item()) / float(tN.item()) / 1e3,
+                      "unit": "Mrays/s", "limits": "the longest paths of the last wave (every rank pays the full bounce-12..50 endgame for 1/N of the "
+                                                   "samples) and the fixed framebuffer reduce"}
+
     if rank == 0:
-        # ---- roofline of the dominant kernel (wf_extend): algorithmic bytes per ray x rays / its event time
+        ncu = load_ncu()
+        # ---- parity of the timed configuration: its own framebuffer against the CPU oracle, same Philox stream
+        parity = None
+        if not args.no_parity:
+            sys.path.insert(0, str(ROOT / "tests"))
+            import support
+            o = support.OracleScene()
+            scenes.build(o, cfg.scene, seed=1, **kwargs)
+            t0 = time.perf_counter()
+            ref, so = o.render(cfg.camera, o.params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0, use_predictors=info.predictors))
+            got = (image_sum / float(total_spp)).cpu().numpy()
+            diff = np.abs(got - ref)
+            total_rays = int(rays.item()) // args.steps
+            parity = {"against": "CPU oracle (oracle/shimmer_oracle.cpp), same seed and Philox stream, outside the timed region",
+                      "image": f"{W}x{H} {total_spp}spp: the framebuffer of the last timed step (default pool, CUDA-graph loop"
+                               + (f", {world} ranks reduced" if world > 1 else "") + ")",
+                      "rmse": float(np.sqrt(np.mean((got - ref) ** 2))), "max_abs": float(diff.max()),
+                      "outliers_gt_1e-3": int((diff.max(axis=2) > 1e-3).sum()), "pixels": W * H,
+                      "rays_gpu": total_rays, "rays_oracle": int(so.rays), "rays_equal": total_rays == int(so.rays),
+                      "gate": "RMSE <= 1e-3 on linear radiance", "pass": bool(np.sqrt(np.mean((got - ref) ** 2)) <= 1e-3),
+                      "oracle_seconds": time.perf_counter() - t0}
+            o.close()
+        # ---- roofline of the dominant kernel
         st_cnt = scene.render_device(cfg.camera, api.make_params(W, H, total_spp, cfg.max_depth, background=info.background, seed=0,
                                                                 sample_begin=0, sample_count=min(spp, 2),
                                                                 flags=capi.RENDER_RAW_SUM | capi.RENDER_COUNT_NODES, pool_paths=args.pool),
                                      fb.data_ptr(), stream.cuda_stream)
-        nodes_per_ray = st_cnt.node_visits / max(1, st_cnt.rays)
-        prims_per_ray = st_cnt.prim_tests / max(1, st_cnt.rays)
-        prim_bytes = {"random-spheres": 32, "cornell-smoke": 32, "showcase": 32}.get(cfg.scene, 48)
-        # B_ray = N_nodes * node bytes + N_prim * S_prim + B_state.  Only B_state = 128 B/ray (the ray
-        # record read by wf_extend and the ray + hit record it writes to a material queue) has to cross HBM; the node and
-        # primitive bytes are served from the TMA-staged shared-memory image (or L2 for scenes that do not fit).
-        hbm_bytes_per_ray = 128.0
-        onchip_bytes_per_ray = nodes_per_ray * 64 + prims_per_ray * prim_bytes
-        ext_ms = sum(s.extend_ms for s in prof_stats)
-        ext_launch = sum(s.extend_launches for s in prof_stats)
-        rays_rank0 = sum(s.rays for s in prof_stats)
-        prof_ms = sum(s.device_ms for s in prof_stats)
-        peak, peak_src, sm_max = load_peaks()
-        achieved = hbm_bytes_per_ray * rays_rank0 / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
-        sm_clk = (clocks.get("sm_mhz") or sm_max) * 1e6
-        inst_per_ray = nodes_per_ray * 2 * 30 + prims_per_ray * 90 + 150  # SURVEY §8d budget (two boxes per 64 B node, f64 sphere x2)
-        issue_peak = 148 * 128 * sm_clk / inst_per_ray / 1e6
-        traffic, traffic_note = None, None
-        tpath = ROOT / "profiles" / "r01_traffic.json"
-        if tpath.exists():
-            tj = json.loads(tpath.read_text())
-            if tj.get("workload") == f"{cfg.key} {W}x{H} {spp}spp":
-                traffic = tj.get("wf_extend_dram_bytes_per_launch")
-                traffic_note = {"captured_launch_rays": tj.get("rays_per_captured_launch"),
-                                "captured_launch_algorithmic_bytes": hbm_bytes_per_ray * tj.get("rays_per_captured_launch", 0),
-                                "source": tj.get("source")}
-        roofline = {"bound": "hbm", "kernel": capi.Stats.EXTEND_KERNELS.get(int(prof_stats[0].extend_variant), "wf_extend") if prof_stats else "wf_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_detail": traffic_note, "peak_source": peak_src,
-                    "algorithmic_bytes_per_ray": hbm_bytes_per_ray,
-                    "algorithmic_bytes_per_launch": hbm_bytes_per_ray * rays_rank0 / max(1, ext_launch),
-                    "onchip_bytes_per_ray": onchip_bytes_per_ray, "nodes_per_ray": nodes_per_ray, "prims_per_ray": prims_per_ray,
-                    "onchip_achieved_gbs": onchip_bytes_per_ray * rays_rank0 / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None,
-                    "extend_ms_per_step": ext_ms / max(1, len(prof_stats)), "extend_share_of_step": ext_ms / prof_ms if prof_ms else None,
-                    "extend_launches_per_step": ext_launch / max(1, len(prof_stats)),
-                    "measured_on": f"{len(prof_stats)} extra steps of the same workload right after the timed steps, CUDA events around every "
-                                   "wf_extend launch (the timed steps carry no per-kernel events; the event pairs themselves add a few us per launch)",
-                    "note": "HBM is not the binding ceiling of this path (SURVEY.md §8d): nodes and primitives are walked in shared memory and the "
-                            "kernel is limited by instruction issue, see issue_roofline; traffic = ncu dram bytes per launch (profiles/)",
-                    "issue_roofline": {"budget_inst_per_ray": inst_per_ray, "sm_mhz": sm_clk / 1e6,
-                                       "peak_mrays": issue_peak, "achieved_mrays_extend_only": rays_rank0 / (ext_ms / 1e3) / 1e6 if ext_ms > 0 else None,
-                                       "frac": (rays_rank0 / (ext_ms / 1e3) / 1e6) / issue_peak if ext_ms > 0 else None}}
+        variant = int(prof_stats[0].extend_variant) if prof_stats else 0
+        kernel = capi.Stats.EXTEND_KERNELS.get(variant, "wf_extend")
+        roofline = roofline_entry(cfg.scene, kernel, variant == 4, st_cnt, prof_stats, clocks, ncu.get(cfg.key, {})) if prof_stats else None
         cpu = None
         if world == 1 and not args.no_cpu:
-            c = run_cpu(args, args.steps_cpu, args.warmup_cpu, budget_s=25.0)
-            cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": c["threads"], "kind": "port", "sample": c["sample"],
-                   "samples_per_s": c["samples_per_s"], "ref_nodes_per_ray": c["nodes_per_ray"], "ref_prims_per_ray": c["prims_per_ray"]}
+            cpu = cpu_entry(run_cpu(cfg, W, H, spp, kwargs, args.steps_cpu, args.warmup_cpu, budget_s=25.0))
+        extra = None
+        if world == 1 and not args.no_configs and args.config == "C1":
+            extra = {}
+            for label, key, kw, with_cpu in EXTRA:
+                t0 = time.perf_counter()
+                try:
+                    extra[label] = measure_extra(label, key, kw, with_cpu, args, api, capi, scenes, torch, dev, stream, flush, clocks, ncu)
+                    extra[label]["bench_seconds"] = time.perf_counter() - t0
+                except Exception as e:  # noqa: BLE001 — one config must not take the headline line down
+                    extra[label] = {"error": f"{type(e).__name__}: {e}"}
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(tot_ms.item()) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (+f64 sphere quadratic)", "data": "synthetic",
-                "config": config_dict(cfg, W, H, spp, args, {"sharding": f"sample-range x{world}", "pool_paths": args.pool or (1 << 24),
-                                                             "scene_device_bytes": scene.device_bytes()}),
+                "config": config_dict(cfg, W, H, spp, world),
+                "run": {"sharding": f"sample-range x{world}", "pool_paths": int(stats[-1].pool_paths), "pool_bytes": int(stats[-1].pool_bytes),
+                        "scene_device_bytes": scene.device_bytes()},
                 "samples_per_s": samples_per_s, "rays_per_step": float(rays.item()) / args.steps,
                 "wall_s_timed_region": wall,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": float(e2e_t.item()) / max(1, len(e2e_ms)),
-                        "what": "shim_commit (flatten + scene H2D) + shim_render into a host framebuffer (D2H), host timer",
+                        "what": ("shim_commit (flatten + scene H2D) + shim_render into a host framebuffer (D2H), host timer" if world == 1 else
+                                 "per rank: shim_commit + render of its sample range; then the NCCL framebuffer sum and rank 0's D2H of the image; "
+                                 "host timer, max over ranks") + "; scene recording incl. the SAH tree build is outside (Bvh::new is outside "
+                                "Renderer::render in the reference too)",
                         "host_framebuffer": "pageable" if args.pageable_fb else "page-locked (shim_host_alloc)"},
                 "gpu_launches": int(sum(s.kernel_launches for s in stats)),
                 "iterations_per_step": float(np.mean([s.iterations for s in stats])),
-                "roofline": roofline, "cpu_baseline": cpu}
+                "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "strong": strong, "configs": extra}
         print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -424,6 +630,13 @@ def main():
     ap.add_argument("--steps-cpu", type=int, default=2)
     ap.add_argument("--warmup-cpu", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline only: skip BASELINE.json's other configurations")
+    ap.add_argument("--extra-samples", type=float, default=1.0e8, help="samples per step of each extra configuration")
+    ap.add_argument("--extra-steps", type=int, default=3)
+    ap.add_argument("--extra-cpu-s", type=float, default=5.0)
+    ap.add_argument("--strong-spp", type=int, default=160)
+    ap.add_argument("--strong-steps", type=int, default=5)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
