@@ -199,10 +199,10 @@ def run_cpu(cfg, W, H, spp, kw, steps, warmup, budget_s, threads=0):
     o = support.OracleScene()
     info = scenes.build(o, cfg.scene, seed=1, **kw)
 
-    # bounded sample: configurations above half a megapixel are timed on a window-preserving reduced image (same camera,
+    # bounded sample: configurations above a megapixel (C3, C5) are timed on a window-preserving reduced image (same camera,
     # same scene, W/k x H/k pixels; rays per sample and the per-ray cost do not depend on the pixel count)
     k = 1
-    while (W // k) * (H // k) > 600_000:
+    while (W // k) * (H // k) > 1_000_000:
         k += 1
     W, H = W // k, H // k
 

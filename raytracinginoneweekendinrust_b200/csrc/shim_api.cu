@@ -72,7 +72,7 @@ struct DeviceGuard {
 // device.  It is kept after commit so that shim_render_multi can replicate the scene on further devices.
 struct SceneBlob {
     std::vector<unsigned char> bytes;
-    size_t o_nodes = 0, o_sph = 0, o_sph_s = 0, o_sph_mat = 0, o_msph = 0, o_rect = 0, o_tri = 0, o_cube = 0, o_obj = 0, o_mat = 0, o_tex = 0,
+    size_t o_nodes = 0, o_snodes = 0, o_sph = 0, o_sph_s = 0, o_sph_mat = 0, o_msph = 0, o_rect = 0, o_tri = 0, o_cube = 0, o_obj = 0, o_mat = 0, o_tex = 0,
            o_img = 0, o_perlin = 0;
     size_t o_handle[5] = {0}, o_rank[5] = {0}, o_leaf[5] = {0}, o_sib[5] = {0};
     int n_objects = 0, n_nodes = 0;
@@ -161,7 +161,8 @@ Wavefront g_wf[SHIM_MAX_DEVICES];
 // what a committed scene owns on the device side: the host blob and one DeviceScene per device it has been used on
 struct shim::DeviceState {
     SceneBlob blob;
-    SmemLayout smem;
+    SmemLayout smem;                   // shared-memory image with the plain 64-byte nodes (total 0: does not fit)
+    SmemLayout smem_signed;            // ... with SNodes, for the one-Bvh kernels (total 0: not built)
     int n_predictors = 0, hrpp_log2 = 21;
     int primary = -1;                  // the device shim_commit uploaded to
     uint32_t kinds_mask = 0;           // material kinds the scene holds (bit k = MatKind k)
@@ -196,7 +197,7 @@ static int upload_scene(shim::DeviceState* st, int device, DeviceScene** out) {
     SceneView& v = d->view;
     memset(&v, 0, sizeof v);
     unsigned char* base = d->base;
-    v.nodes = (const DevNode*)(base + b.o_nodes); v.sph = (const double*)(base + b.o_sph); v.sph_s = (const f4*)(base + b.o_sph_s);
+    v.nodes = (const DevNode*)(base + b.o_nodes); v.snodes = st->smem_signed.total ? (const SNode*)(base + b.o_snodes) : nullptr; v.sph = (const double*)(base + b.o_sph); v.sph_s = (const f4*)(base + b.o_sph_s);
     v.sph_mat = (const int*)(base + b.o_sph_mat); v.msph = (const f4*)(base + b.o_msph); v.rect = (const f4*)(base + b.o_rect);
     v.tri = (const f4*)(base + b.o_tri); v.cube = (const f4*)(base + b.o_cube); v.objects = (const DevObject*)(base + b.o_obj);
     v.materials = (const f4*)(base + b.o_mat); v.textures = (const f4*)(base + b.o_tex);
@@ -238,9 +239,35 @@ SHIM_API int shim_commit(shim_scene* s) {
     int device = -1;
     CU(cudaGetDevice(&device));
     if (device < 0 || device >= SHIM_MAX_DEVICES) return set_err(SHIM_ERR_UNSUPPORTED, "device ordinal out of range");
-    const FlatScene& f = s->flat;
     if (s->dev) { device_state_release(s->dev); s->dev = nullptr; }
     std::unique_ptr<shim::DeviceState> st(new shim::DeviceState());
+    auto layout = [&](SmemLayout& L, const FlatScene& f, bool signed_nodes) {
+        // shared-memory image of what the closest-hit kernels walk; total = 0 when it cannot fit any sm_100a block
+        memset(&L, 0, sizeof L);
+        const size_t node_bytes = f.nodes.size() * (signed_nodes ? sizeof(SNode) : sizeof(DevNode));
+        uint32_t off = 0;
+        auto place = [&](uint32_t& o, uint32_t& by, size_t bytes) { o = off; by = (uint32_t)bytes; off += (uint32_t)((bytes + 127) & ~(size_t)127); };
+        size_t tot = node_bytes + f.sph.size() * 8 + (f.msph.size() + f.rect.size() + f.tri.size() + f.cube.size()) * 16 +
+                     f.objects.size() * sizeof(DevObject) + f.sph_mat.size() * 4 + 16;
+        if (tot > 220 * 1024) return;
+        place(L.off_nodes, L.bytes_nodes, node_bytes);
+        place(L.off_sph, L.bytes_sph, f.sph.size() * 8);
+        place(L.off_msph, L.bytes_msph, f.msph.size() * 16);
+        place(L.off_rect, L.bytes_rect, f.rect.size() * 16);
+        place(L.off_tri, L.bytes_tri, f.tri.size() * 16);
+        place(L.off_cube, L.bytes_cube, f.cube.size() * 16);
+        place(L.off_objects, L.bytes_objects, f.objects.size() * sizeof(DevObject));
+        place(L.off_sph_mat, L.bytes_sph_mat, (f.sph_mat.size() * 4 + 15) & ~(size_t)15);   // bulk copies move 16-byte units (the blob pads every array)
+        L.total = off;
+        L.signed_nodes = signed_nodes ? 1u : 0u;
+    };
+    layout(st->smem, s->flat, false);
+    // one plain Bvh and nothing else: the one-Bvh kernels walk the signed node layout (shim_types.h) in shared memory
+    if (s->flat.objects.size() == 1 && s->flat.objects[0].kind == OBJ_BVH && (s->flat.objects[0].flags & ~OBJ_PREDICTOR) == 0) {
+        layout(st->smem_signed, s->flat, true);
+        if (st->smem_signed.total) s->flat.build_signed_nodes();
+    }
+    const FlatScene& f = s->flat;
     SceneBlob& b = st->blob;
     auto put = [&](const void* src, size_t bytes) -> size_t {
         size_t off = (b.bytes.size() + 255) & ~(size_t)255;
@@ -249,6 +276,7 @@ SHIM_API int shim_commit(shim_scene* s) {
         return off;
     };
     b.o_nodes = put(f.nodes.data(), f.nodes.size() * sizeof(DevNode));
+    b.o_snodes = put(f.snodes.data(), f.snodes.size() * sizeof(SNode));
     b.o_sph = put(f.sph.data(), f.sph.size() * 8); b.o_sph_s = put(f.sph_s.data(), f.sph_s.size() * 16);
     b.o_sph_mat = put(f.sph_mat.data(), f.sph_mat.size() * 4);
     b.o_msph = put(f.msph.data(), f.msph.size() * 16); b.o_rect = put(f.rect.data(), f.rect.size() * 16);
@@ -269,25 +297,6 @@ SHIM_API int shim_commit(shim_scene* s) {
     for (size_t i = 0; i + 1 < f.materials.size(); i += 2) {
         const int kind = f2i(f.materials[i].x);
         if (kind >= 0 && kind < MAT_KINDS) st->kinds_mask |= 1u << kind;
-    }
-    {   // shared-memory image of what the closest-hit kernels walk; total = 0 when it cannot fit any sm_100a block
-        SmemLayout& L = st->smem;
-        memset(&L, 0, sizeof L);
-        uint32_t off = 0;
-        auto place = [&](uint32_t& o, uint32_t& by, size_t bytes) { o = off; by = (uint32_t)bytes; off += (uint32_t)((bytes + 127) & ~(size_t)127); };
-        size_t tot = f.nodes.size() * sizeof(DevNode) + f.sph.size() * 8 + (f.msph.size() + f.rect.size() + f.tri.size() + f.cube.size()) * 16 +
-                     f.objects.size() * sizeof(DevObject) + f.sph_mat.size() * 4 + 16;
-        if (tot <= 220 * 1024) {
-            place(L.off_nodes, L.bytes_nodes, f.nodes.size() * sizeof(DevNode));
-            place(L.off_sph, L.bytes_sph, f.sph.size() * 8);
-            place(L.off_msph, L.bytes_msph, f.msph.size() * 16);
-            place(L.off_rect, L.bytes_rect, f.rect.size() * 16);
-            place(L.off_tri, L.bytes_tri, f.tri.size() * 16);
-            place(L.off_cube, L.bytes_cube, f.cube.size() * 16);
-            place(L.off_objects, L.bytes_objects, f.objects.size() * sizeof(DevObject));
-            place(L.off_sph_mat, L.bytes_sph_mat, (f.sph_mat.size() * 4 + 15) & ~(size_t)15);   // bulk copies move 16-byte units (the blob pads every array)
-            L.total = off;
-        }
     }
     st->primary = device;
     DeviceScene* ds = nullptr;
@@ -372,13 +381,16 @@ static void choose_variant(const shim_scene* s, const shim::DeviceState* st, con
     if (!use_smem) k.smem.total = 0;
     *use_smem_out = use_smem;
     k.solo = 0; k.solo_only = -1; k.fused_generate = 0; k.trace_pipeline = 0;
-    if (use_smem && !k.count_nodes && !k.use_hrpp && !s->has_media && f.objects.size() == 1 && f.objects[0].kind == OBJ_BVH &&
+    const bool signed_fits = st->smem_signed.total != 0 && (int)st->smem_signed.total <= w.max_smem - 1024 && !sw.no_smem;
+    if (signed_fits && !k.count_nodes && !k.use_hrpp && !s->has_media && f.objects.size() == 1 && f.objects[0].kind == OBJ_BVH &&
         (f.objects[0].flags & ~OBJ_PREDICTOR) == 0 && !sw.no_solo) {
         const bool spheres_only = f.msph.empty() && f.rect.empty() && f.tri.empty() && f.cube.empty() && !sw.solo_any;
         k.solo_only = spheres_only ? (int)PT_SPHERE : -1;
         k.solo = spheres_only ? SHIM_SOLO_SPHERE_THREADS : SHIM_SOLO_ANY_THREADS;   // 72 / 80 registers, no spills
         k.fused_generate = sw.no_fuse ? 0 : 1;
         if (!sw.no_trace) { k.trace_pipeline = k.solo; k.fused_generate = 1; }   // wf_generate is not part of this pipeline
+        k.smem = st->smem_signed;   // the one-Bvh kernels walk SNodes
+        *use_smem_out = true;
     }
     k.bvh1_tri_threads = 0;
     if (k.bvh1_index >= 0 && f.sph_s.empty() && f.msph.empty() && f.cube.empty() && !f.tri.empty() && !sw.no_bvh1_tri) {

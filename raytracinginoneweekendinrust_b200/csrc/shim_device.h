@@ -181,6 +181,7 @@ struct RayCtx {
     Ray r;      // ray as the shape sees it (after Translate / RotateY, instance.rs)
     f3 inv_d;   // 1/d with |d| clamped away from 0 so that the products below stay finite
     f3 o_inv;   // -o * inv_d: a slab plane distance is one fma(plane, inv_d, o_inv)
+    int soff[3]; // SNode walks: byte offset of the ray's {near_l, near_r, far_l, far_r} planes of axis k inside a node
 };
 SHIM_HD f3 rot_y(f3 v, float s, float c) { return mk3(c * v.x - s * v.z, v.y, s * v.x + c * v.z); }       // instance.rs:104-110
 SHIM_HD f3 rot_y_back(f3 v, float s, float c) { return mk3(c * v.x + s * v.z, v.y, -s * v.x + c * v.z); } // instance.rs:125-134
@@ -200,6 +201,9 @@ SHIM_HD void make_ctx(RayCtx& c, const Ray& r) {
     c.r = r;
     c.inv_d = mk3(safe_rcp(r.d.x), safe_rcp(r.d.y), safe_rcp(r.d.z));
     c.o_inv = mk3(-(r.o.x * c.inv_d.x), -(r.o.y * c.inv_d.y), -(r.o.z * c.inv_d.z));
+    c.soff[0] = signbit_f(c.inv_d.x) ? 16 : 0;
+    c.soff[1] = signbit_f(c.inv_d.y) ? 48 : 32;
+    c.soff[2] = signbit_f(c.inv_d.z) ? 80 : 64;
 }
 
 struct TraceCounters { uint32_t nodes, prims, hrpp_tp, hrpp_fp, hrpp_none; };
@@ -371,7 +375,13 @@ SHIM_HD bool tie_goes_to_candidate(const SceneView& sv, const RayCtx& c, float t
 }
 
 #define SHIM_STACK_END 0x7fffffff
-template <bool COUNT, int ONLY = -1>
+SHIM_HD float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }   // FMNMX3 on sm_100a
+SHIM_HD float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// SIGNED: walk sv.snodes (SNode, see shim_types.h); start_node and every non-negative reference are then byte offsets.
+// Both layouts visit the same nodes in the same order and return the same hit: for a box with min <= max and a finite
+// reciprocal the plane the sign picks IS the smaller of the two products (fma is monotonic), and max/min are
+// associative.
+template <bool COUNT, int ONLY = -1, bool SIGNED = false>
 SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, float t_min, float t_max, BvhBest& best,
                          TraceCounters* cnt) {
     best.t = t_max; best.prim = 0; best.face = 0; best.any = false;
@@ -383,24 +393,62 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
     int stack[SHIM_BVH_STACK];
     int sp = 0;
     int cur = start_node;  // >= 0 inner node, < 0 ~prim_ref, SHIM_STACK_END when done
+#if defined(__CUDA_ARCH__)
+    uint32_t p0 = 0, px = 0, py = 0, pz = 0;
+    if (SIGNED) {   // the SNode walk lives in shared memory (wf_extend_solo / wf_trace_solo stage sv.snodes there)
+        p0 = (uint32_t)__cvta_generic_to_shared(sv.snodes);
+        px = p0 + (uint32_t)c.soff[0]; py = p0 + (uint32_t)c.soff[1]; pz = p0 + (uint32_t)c.soff[2];
+        // opaque to the optimiser: otherwise it re-derives the three offsets from the direction signs in every
+        // iteration (ten address instructions per node) instead of keeping three registers
+        asm volatile("" : "+r"(px), "+r"(py), "+r"(pz));
+    }
+#endif
     for (;;) {
         while (cur >= 0 && cur != SHIM_STACK_END) {
-            const DevNode& n = sv.nodes[cur];
-            f4 na = n.a, nb = n.b, nc = n.c;
-            i4 nd = n.d;
-            if (COUNT) cnt->nodes++;
             float tl, tr;
-            bool hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, t_min, t_cull, tl);
-            bool hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, t_min, t_cull, tr);
-            hr = hr && nd.y != CHILD_NONE;
+            bool hl, hr;
+            int left, right;
+            if (SIGNED) {
+                f4 X, Y, Z;
+                i4 nd;
+#if defined(__CUDA_ARCH__)
+                // shared-memory addresses of the ray's plane quadruples: one add per load (px, py, pz are per-ray)
+                asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(X.x), "=f"(X.y), "=f"(X.z), "=f"(X.w) : "r"(px + (uint32_t)cur));
+                asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Y.x), "=f"(Y.y), "=f"(Y.z), "=f"(Y.w) : "r"(py + (uint32_t)cur));
+                asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Z.x), "=f"(Z.y), "=f"(Z.z), "=f"(Z.w) : "r"(pz + (uint32_t)cur));
+                asm("ld.shared.v2.s32 {%0, %1}, [%2+96];" : "=r"(nd.x), "=r"(nd.y) : "r"(p0 + (uint32_t)cur));
+#else
+                const char* nb = reinterpret_cast<const char*>(sv.snodes) + cur;
+                X = *reinterpret_cast<const f4*>(nb + c.soff[0]);
+                Y = *reinterpret_cast<const f4*>(nb + c.soff[1]);
+                Z = *reinterpret_cast<const f4*>(nb + c.soff[2]);
+                nd = *reinterpret_cast<const i4*>(nb + 96);
+#endif
+                tl = fmaxf(max3f(slab_plane(X.x, c.inv_d.x, c.o_inv.x), slab_plane(Y.x, c.inv_d.y, c.o_inv.y), slab_plane(Z.x, c.inv_d.z, c.o_inv.z)), t_min);
+                tr = fmaxf(max3f(slab_plane(X.y, c.inv_d.x, c.o_inv.x), slab_plane(Y.y, c.inv_d.y, c.o_inv.y), slab_plane(Z.y, c.inv_d.z, c.o_inv.z)), t_min);
+                const float fl = fminf(min3f(slab_plane(X.z, c.inv_d.x, c.o_inv.x), slab_plane(Y.z, c.inv_d.y, c.o_inv.y), slab_plane(Z.z, c.inv_d.z, c.o_inv.z)), t_cull);
+                const float fr = fminf(min3f(slab_plane(X.w, c.inv_d.x, c.o_inv.x), slab_plane(Y.w, c.inv_d.y, c.o_inv.y), slab_plane(Z.w, c.inv_d.z, c.o_inv.z)), t_cull);
+                hl = !(fl < tl);
+                hr = !(fr < tr) && nd.y != CHILD_NONE;
+                left = nd.x; right = nd.y;
+            } else {
+                const DevNode& n = sv.nodes[cur];
+                f4 na = n.a, nb = n.b, nc = n.c;
+                i4 nd = n.d;
+                hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, t_min, t_cull, tl);
+                hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, t_min, t_cull, tr);
+                hr = hr && nd.y != CHILD_NONE;
+                left = nd.x; right = nd.y;
+            }
+            if (COUNT) cnt->nodes++;
             if (hl && hr) {
                 bool swap = tr < tl;
-                cur = swap ? nd.y : nd.x;
-                if (sp < SHIM_BVH_STACK) stack[sp++] = swap ? nd.x : nd.y;
+                cur = swap ? right : left;
+                if (sp < SHIM_BVH_STACK) stack[sp++] = swap ? left : right;
             } else if (hl) {
-                cur = nd.x;
+                cur = left;
             } else if (hr) {
-                cur = nd.y;
+                cur = right;
             } else {
                 cur = sp > 0 ? stack[--sp] : SHIM_STACK_END;
             }
@@ -618,13 +666,14 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
 
 // closest_hit for a world that is exactly one plain Bvh (no Translate / RotateY / medium / predictor), e.g. the
 // Book-1 scene (main.rs:185-251): no object loop, no object-space ray, fewer live registers in wf_extend_solo.
-template <bool COUNT, int ONLY = -1>
+template <bool COUNT, int ONLY = -1, bool SIGNED = false>
 SHIM_HD Hit closest_hit_solo(const SceneView& sv, const Ray& ray, float t_min, float t_max, TraceCounters* cnt) {
     Hit h; h.t = t_max; h.obj = -1; h.prim = 0; h.face = 0;
     RayCtx c;
     make_ctx(c, ray);
     BvhBest best;
-    if (bvh_closest<COUNT, ONLY>(sv, sv.objects[0].ref, c, t_min, t_max, best, cnt)) { h.t = best.t; h.obj = 0; h.prim = best.prim; h.face = best.face; }
+    const int root = SIGNED ? sv.objects[0].ref * (int)sizeof(SNode) : sv.objects[0].ref;
+    if (bvh_closest<COUNT, ONLY, SIGNED>(sv, root, c, t_min, t_max, best, cnt)) { h.t = best.t; h.obj = 0; h.prim = best.prim; h.face = best.face; }
     return h;
 }
 

@@ -43,6 +43,7 @@ struct SmemLayout {
     uint32_t off_nodes, off_sph, off_msph, off_rect, off_tri, off_cube, off_objects, off_sph_mat;
     uint32_t bytes_nodes, bytes_sph, bytes_msph, bytes_rect, bytes_tri, bytes_cube, bytes_objects, bytes_sph_mat;
     uint32_t total;  // 0 = scene does not fit: walk it in global memory (L2)
+    uint32_t signed_nodes;  // the node region holds SNodes (sv.snodes): layout of the one-Bvh kernels
 };
 
 struct WfParams {
@@ -233,7 +234,7 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
             }
             TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
             Hit h; h.obj = -1; h.t = 0; h.prim = 0; h.face = 0;
-            if (!poisoned) h = SOLO ? closest_hit_solo<COUNT, ONLY>(sv, r, 0.001f, SHIM_INF, &tc) : closest_hit<COUNT, HRPP, HASBVH>(sv, r, 0.001f, SHIM_INF, rng, &tc);
+            if (!poisoned) h = SOLO ? closest_hit_solo<COUNT, ONLY, true>(sv, r, 0.001f, SHIM_INF, &tc) : closest_hit<COUNT, HRPP, HASBVH>(sv, r, 0.001f, SHIM_INF, rng, &tc);
             nodes += tc.nodes; prims += tc.prims; h_tp += tc.hrpp_tp; h_fp += tc.hrpp_fp; h_none += tc.hrpp_none;
             if (poisoned) {
                 // path ends without a contribution
@@ -281,6 +282,9 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
 }
 
 // TMA-stages the arrays the walk reads into the block's shared memory (scene images up to ~220 KB)
+// SIGNED: the node region holds SNodes (p.smem.signed_nodes; the one-Bvh kernels) - a template parameter so that the
+// compiler knows which of the two node pointers is a shared-memory address (LDS instead of generic loads)
+template <bool SIGNED = false>
 __device__ __forceinline__ SceneView stage_scene(const WfParams& p, unsigned char* smem, uint64_t* bar) {
     SceneView sv = p.sv;
     if (threadIdx.x == 0) mbar_init(bar, 1);
@@ -288,7 +292,7 @@ __device__ __forceinline__ SceneView stage_scene(const WfParams& p, unsigned cha
     if (threadIdx.x == 0) {
         const SmemLayout& L = p.smem;
         mbar_expect_tx(bar, L.bytes_nodes + L.bytes_sph + L.bytes_msph + L.bytes_rect + L.bytes_tri + L.bytes_cube + L.bytes_objects + L.bytes_sph_mat);
-        if (L.bytes_nodes) bulk_g2s(smem + L.off_nodes, p.sv.nodes, L.bytes_nodes, bar);
+        if (L.bytes_nodes) bulk_g2s(smem + L.off_nodes, SIGNED ? (const void*)p.sv.snodes : (const void*)p.sv.nodes, L.bytes_nodes, bar);
         if (L.bytes_sph) bulk_g2s(smem + L.off_sph, p.sv.sph, L.bytes_sph, bar);
         if (L.bytes_msph) bulk_g2s(smem + L.off_msph, p.sv.msph, L.bytes_msph, bar);
         if (L.bytes_rect) bulk_g2s(smem + L.off_rect, p.sv.rect, L.bytes_rect, bar);
@@ -297,7 +301,8 @@ __device__ __forceinline__ SceneView stage_scene(const WfParams& p, unsigned cha
         if (L.bytes_objects) bulk_g2s(smem + L.off_objects, p.sv.objects, L.bytes_objects, bar);
         if (L.bytes_sph_mat) bulk_g2s(smem + L.off_sph_mat, p.sv.sph_mat, L.bytes_sph_mat, bar);
     }
-    sv.nodes = reinterpret_cast<const DevNode*>(smem + p.smem.off_nodes);
+    if (SIGNED) sv.snodes = reinterpret_cast<const SNode*>(smem + p.smem.off_nodes);
+    else sv.nodes = reinterpret_cast<const DevNode*>(smem + p.smem.off_nodes);
     sv.sph = reinterpret_cast<const double*>(smem + p.smem.off_sph);
     sv.msph = reinterpret_cast<const f4*>(smem + p.smem.off_msph);
     sv.rect = reinterpret_cast<const f4*>(smem + p.smem.off_rect);
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_solo() {
     if (blockIdx.x * blockDim.x >= n) return;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
-    SceneView sv = stage_scene(p, smem, &bar);
+    SceneView sv = stage_scene<true>(p, smem, &bar);
     extend_rays<COUNT, false, false, true, ONLY, true, FUSE>(p, sv, cur, n);
 }
 
@@ -753,7 +758,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_trace_solo() {
     if (blockIdx.x * blockDim.x >= total) return;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
-    const SceneView sv = stage_scene(p, smem, &bar);
+    const SceneView sv = stage_scene<true>(p, smem, &bar);
     const unsigned long long gen_first = *cnt64(p.cnt, C64_GEN_FIRST);
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t* out_cnt = mq_counts(p, 1 - cur);
@@ -775,7 +780,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_trace_solo() {
             Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
             if (!ray_has_nan(r)) {   // see extend_rays
                 TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
-                const Hit h = closest_hit_solo<false, ONLY>(sv, r, 0.001f, SHIM_INF, &tc);
+                const Hit h = closest_hit_solo<false, ONLY, true>(sv, r, 0.001f, SHIM_INF, &tc);   // SNodes in shared memory
                 if (h.obj < 0) {  // ray.rs:60
                     if (p.bg[0] != 0.0f || p.bg[1] != 0.0f || p.bg[2] != 0.0f) {
                         float* a = p.accum + 3 * (size_t)(uint32_t)f2i(t.w);

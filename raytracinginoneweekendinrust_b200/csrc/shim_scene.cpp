@@ -575,7 +575,7 @@ int SceneBuilder::flatten(FlatScene& fs) {
 SceneView FlatScene::view() const {
     SceneView v;
     memset(&v, 0, sizeof v);
-    v.nodes = nodes.data(); v.sph = sph.data(); v.sph_s = sph_s.data(); v.sph_mat = sph_mat.data();
+    v.nodes = nodes.data(); v.snodes = snodes.empty() ? nullptr : snodes.data(); v.sph = sph.data(); v.sph_s = sph_s.data(); v.sph_mat = sph_mat.data();
     v.msph = msph.data(); v.rect = rect.data(); v.tri = tri.data(); v.cube = cube.data();
     v.objects = objects.data(); v.materials = materials.data(); v.textures = textures.data();
     v.images = images.data(); v.perlin = perlin.data();
@@ -583,8 +583,24 @@ SceneView FlatScene::view() const {
     v.n_objects = (int)objects.size(); v.n_nodes = (int)nodes.size();
     return v;
 }
+// DevNode -> SNode (shim_types.h): the planes of each axis in both orders, child node references as byte offsets
+void FlatScene::build_signed_nodes() {
+    snodes.resize(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const DevNode& n = nodes[i];
+        const float lmn[3] = {n.a.x, n.a.y, n.a.z}, lmx[3] = {n.a.w, n.b.x, n.b.y};
+        const float rmn[3] = {n.b.z, n.b.w, n.c.x}, rmx[3] = {n.c.y, n.c.z, n.c.w};
+        SNode& s = snodes[i];
+        for (int k = 0; k < 3; ++k) {
+            s.ax[2 * k] = f4{lmn[k], rmn[k], lmx[k], rmx[k]};
+            s.ax[2 * k + 1] = f4{lmx[k], rmx[k], lmn[k], rmn[k]};
+        }
+        s.d = i4{n.d.x >= 0 ? n.d.x * (int)sizeof(SNode) : n.d.x, n.d.y >= 0 ? n.d.y * (int)sizeof(SNode) : n.d.y, n.d.z, 0};
+    }
+}
+
 uint64_t FlatScene::bytes() const {
-    uint64_t b = nodes.size() * sizeof(DevNode) + sph.size() * 8 + sph_s.size() * 16 + sph_mat.size() * 4 +
+    uint64_t b = nodes.size() * sizeof(DevNode) + snodes.size() * sizeof(SNode) + sph.size() * 8 + sph_s.size() * 16 + sph_mat.size() * 4 +
                  (msph.size() + rect.size() + tri.size() + cube.size() + materials.size() + textures.size()) * 16 +
                  objects.size() * sizeof(DevObject) + images.size() + perlin.size();
     for (int i = 0; i < 5; ++i) b += handle[i].size() * 16;

@@ -47,6 +47,8 @@ struct HostHittable {
 // Flattened scene, host copy; uploaded verbatim.
 struct FlatScene {
     std::vector<DevNode> nodes;
+    std::vector<SNode> snodes;       // `nodes` in the signed layout (build_signed_nodes; empty = not built)
+    void build_signed_nodes();
     std::vector<double> sph;
     std::vector<f4> sph_s;
     std::vector<int> sph_mat;

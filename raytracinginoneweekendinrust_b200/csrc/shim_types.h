@@ -64,6 +64,16 @@ struct alignas(16) DevNode {
     i4 d;  // left ref, right ref (>=0 node, <0 ~prim_ref), parent, unused
 };
 
+// The same node for walks in shared memory (one-Bvh worlds): per axis the four child planes twice, once as
+// {l.min, r.min, l.max, r.max} and once as {l.max, r.max, l.min, r.min}, so that ONE 16-byte load at offset 0 or 16 -
+// chosen once per ray from the sign of its direction - returns {near_l, near_r, far_l, far_r} and the slab test needs
+// no min/max to order the planes (12 fewer instructions per node; the ALU pipe is the busiest in the walk).
+// Child references >= 0 are BYTE offsets of the child node (index * sizeof(SNode)), < 0 ~prim_ref as in DevNode.
+struct alignas(16) SNode {
+    f4 ax[6];  // [2 * axis + (direction negative ? 1 : 0)]
+    i4 d;      // left ref, right ref, parent (node index), unused
+};
+
 enum ObjFlags { OBJ_TRANSLATE = 1, OBJ_ROTATE = 2, OBJ_MEDIUM = 4, OBJ_PREDICTOR = 8 };
 enum ObjKind { OBJ_PRIM = 0, OBJ_BVH = 1 };
 
@@ -80,6 +90,7 @@ struct alignas(16) DevObject {
 
 struct SceneView {
     const DevNode* nodes;
+    const SNode* snodes;    // the nodes again in the signed layout, or null (built for scenes that fit shared memory)
     const double* sph;      // 4 per sphere
     const f4* sph_s;
     const int* sph_mat;

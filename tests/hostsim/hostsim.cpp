@@ -85,6 +85,28 @@ extern "C" __attribute__((visibility("default"))) int hs_trace_closest(shim_scen
     return 0;
 }
 
+// closest hit of a one-Bvh world with closest_hit_solo, on the plain node layout or the signed one (SNode):
+// the two must agree bit for bit, counters included
+extern "C" __attribute__((visibility("default"))) int hs_trace_closest_solo(shim_scene* s, const float* rays, int64_t n, float t_min,
+                                                                           float t_max, int signed_nodes, int32_t* prim, float* t,
+                                                                           uint64_t* counters) {
+    if (s->flat.objects.size() != 1 || s->flat.objects[0].kind != OBJ_BVH || s->flat.objects[0].flags != 0) return -1;
+    if (signed_nodes && s->flat.snodes.empty()) s->flat.build_signed_nodes();
+    SceneView sv = view_of(s);
+    uint64_t nodes = 0, prims = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* q = rays + i * 7;
+        Ray r; r.o = mk3(q[0], q[1], q[2]); r.d = mk3(q[3], q[4], q[5]); r.time = q[6];
+        TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
+        Hit h = signed_nodes ? closest_hit_solo<true, -1, true>(sv, r, t_min, t_max, &tc) : closest_hit_solo<true, -1, false>(sv, r, t_min, t_max, &tc);
+        nodes += tc.nodes; prims += tc.prims;
+        prim[i] = hit_handle(sv, h);
+        t[i] = h.obj < 0 ? INFINITY : h.t;
+    }
+    if (counters) { counters[0] = (uint64_t)n; counters[1] = nodes; counters[2] = prims; }
+    return 0;
+}
+
 // the wavefront's per-path arithmetic, executed path by path (same order of operations as
 // wf_generate / wf_extend / wf_shade)
 extern "C" __attribute__((visibility("default"))) int hs_sample_radiance(shim_scene* s, const shim_camera* cam,

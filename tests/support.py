@@ -96,6 +96,8 @@ def hostsim_lib():
         lib.hs_commit.argtypes = [_P]
         lib.hs_trace_closest.restype = _I
         lib.hs_trace_closest.argtypes = [_P, _P, C.c_int64, _F, _F, C.c_uint64, _P, _P, _P]
+        lib.hs_trace_closest_solo.restype = _I
+        lib.hs_trace_closest_solo.argtypes = [_P, _P, C.c_int64, _F, _F, _I, _P, _P, _P]
         lib.hs_sample_radiance.restype = _I
         lib.hs_sample_radiance.argtypes = [_P, C.POINTER(Camera), C.POINTER(RenderParams), _P, C.c_int64, _P, _P]
         lib.hs_texture_value.restype = None
@@ -178,6 +180,16 @@ class HostSimScene(capi.SceneHandle):
         prim = np.empty(n, np.int32); t = np.empty(n, np.float32); cnt = np.zeros(3, np.uint64)
         self.lib.hs_trace_closest(self.ptr, rays.ctypes.data, n, t_min, t_max, seed, prim.ctypes.data, t.ctypes.data, cnt.ctypes.data)
         return (prim, t, cnt) if counters else (prim, t)
+
+    def trace_closest_solo(self, rays, signed_nodes, t_min=0.001, t_max=float("inf")):
+        """closest_hit_solo (one-Bvh worlds) on the plain or the signed node layout; returns ids, t and the counters."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 7)
+        n = rays.shape[0]
+        prim = np.empty(n, np.int32); t = np.empty(n, np.float32); cnt = np.zeros(3, np.uint64)
+        rc = self.lib.hs_trace_closest_solo(self.ptr, rays.ctypes.data, n, t_min, t_max, 1 if signed_nodes else 0, prim.ctypes.data,
+                                            t.ctypes.data, cnt.ctypes.data)
+        assert rc == 0, "not a one-Bvh world"
+        return prim, t, cnt
 
     def enable_predictors(self, log2=16):
         return self.lib.hs_enable_predictors(self.ptr, log2)

@@ -81,3 +81,36 @@ def test_edge_rays():
     assert po[0] == -1 and np.isinf(to[0]) and po[1] >= 0
     p, t = h.trace_closest(np.zeros((0, 7), np.float32))
     assert len(p) == 0
+
+
+@pytest.mark.parametrize("reference_tree", [False, True])
+@pytest.mark.parametrize("name", ["random-spheres", "random-moving-spheres"])
+def test_signed_node_layout_walks_the_same_nodes(name, reference_tree):
+    """The shared-memory node layout of the one-Bvh kernels (SNode: planes pre-ordered by the ray's direction signs)
+    against the plain 64-byte node and against the oracle: same ids, bit-equal t, the same node and primitive
+    counts - including rays with zero direction components and rays inside the boxes (aabb.rs:28-41 semantics)."""
+    o, h = support.OracleScene(), support.HostSimScene()
+    info = scenes.build(o, name, seed=1)
+    h.set_device_bvh(reference_tree)
+    scenes.build(h, name, seed=1)
+    cam = T.CAMERAS[name]
+    W, H, spp = 160, 120, 4
+    po = o.params(W, H, spp, 50, background=info.background, seed=21, iterative=True)
+    rays = o.record_path_rays(cam, po, support.random_xys(W, H, spp, 3000, seed=2), 40000)
+    rs = np.random.RandomState(3)
+    axis = rays[:2000].copy()                      # axis-parallel and zero-component directions, negative zeros too
+    for i in range(len(axis)):
+        k = rs.randint(0, 3)
+        axis[i, 3 + k] = [0.0, -0.0][rs.randint(0, 2)]
+        if rs.rand() < 0.3:
+            axis[i, 3 + (k + 1) % 3] = [0.0, -0.0][rs.randint(0, 2)]
+    rays = np.concatenate([rays, axis])
+    p_ref, t_ref = o.trace_closest(rays, seed=21)
+    p0, t0, c0 = h.trace_closest_solo(rays, signed_nodes=False)
+    p1, t1, c1 = h.trace_closest_solo(rays, signed_nodes=True)
+    np.testing.assert_array_equal(p0, p1)
+    np.testing.assert_array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    assert list(c0) == list(c1)                    # same node visits and primitive tests
+    np.testing.assert_array_equal(p_ref, p1)
+    hit = p_ref >= 0
+    np.testing.assert_array_equal(t_ref[hit].view(np.uint32), t1[hit].view(np.uint32))
