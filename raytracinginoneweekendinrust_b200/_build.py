@@ -25,13 +25,15 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+def build_cuda(force: bool = False, verbose: bool = False, out: Path | None = None, defines=()) -> Path:
+    """``out`` / ``defines``: experiment builds (A/B runs under gpurun select one with SHIMMER_B200_LIB)."""
     srcs = [CSRC / s for s in CUDA_SOURCES]
     deps = srcs + [CSRC / h for h in HEADERS] + [PKG.parent / "include" / "shimmer_b200.h"]
-    if force or _stale(LIB, deps):
-        LIB.parent.mkdir(parents=True, exist_ok=True)
-        cmd = [NVCC, *NVCC_FLAGS, "-o", str(LIB), *map(str, srcs)]
+    lib = Path(out) if out else LIB
+    if force or _stale(lib, deps):
+        lib.parent.mkdir(parents=True, exist_ok=True)
+        cmd = [NVCC, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", str(lib), *map(str, srcs)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
-    return LIB
+    return lib

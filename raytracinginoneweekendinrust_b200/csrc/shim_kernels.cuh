@@ -318,7 +318,9 @@ __device__ __forceinline__ SceneView stage_scene(const WfParams& p, unsigned cha
 #define SHIM_EXTEND_THREADS 640
 #endif
 // threads per block of the specialised kernels (one persistent block per SM; measured in round 1)
+#ifndef SHIM_SOLO_SPHERE_THREADS
 #define SHIM_SOLO_SPHERE_THREADS 896   // sphere-only Bvh worlds: 72 registers
+#endif
 #define SHIM_SOLO_ANY_THREADS 768      // one plain Bvh of mixed primitives: 80 registers
 #define SHIM_LIST_THREADS 1024         // worlds without a Bvh: 64 registers
 #define SHIM_BVH1_TRI_THREADS 896      // one triangle-only Bvh among rects
