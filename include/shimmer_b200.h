@@ -114,7 +114,9 @@ typedef struct shim_camera {
 
 /* ---- render: Renderer::render, renderer.rs:42-105 -------------------------------------- */
 enum { SHIM_RENDER_RAW_SUM = 1, SHIM_RENDER_PREDICTORS = 2, SHIM_RENDER_COUNT_NODES = 4,
-       SHIM_RENDER_PROFILE = 8 /* CUDA events around every wf_extend launch -> stats.extend_ms */ };
+       SHIM_RENDER_PROFILE = 8 /* CUDA events around every wf_extend launch -> stats.extend_ms */,
+       SHIM_RENDER_KEEP_PREDICTORS = 16 /* with PREDICTORS: keep what earlier renders of this scene learnt (the reference
+                                           builds fresh Predictors with every scene, bvh.rs:69-81: default = clear) */ };
 typedef struct shim_render_params {
     int32_t width, height;         /* Renderer::new */
     int32_t samples_per_pixel;     /* divisor of the mean */
@@ -186,6 +188,11 @@ int shim_trace_closest_device(shim_scene* s, const float* d_rays, int64_t n, flo
 int shim_tile_layout(int image_width, int image_height, int tile_width, int tile_height, int32_t* out4, int cap);
 /* Camera::new derived fields: origin, horizontal, vertical, lower_left_corner, u, v (18 floats), lens_radius, t0, t1 */
 int shim_camera_fields(const shim_camera* cam, float* out21);
+/* Aabb::hit, aabb.rs:28-41, evaluated the way the kernels do it (reciprocal direction, fused multiply-add per
+ * plane, a zero direction component clamped to +-1e-30 instead of an infinite reciprocal): 1 hit, 0 miss.
+ * layout 0: the 64-byte node's slab test; layout 1: the signed shared-memory node of the one-Bvh kernels. */
+int shim_aabb_hit(const float* min3, const float* max3, const float* origin3, const float* direction3, float t_min, float t_max,
+                  int layout);
 /* hrpp::hash, hrpp.rs:174-193 */
 uint64_t shim_hrpp_hash(const float* origin3, const float* direction3);
 /* Renderer::write_ppm, renderer.rs:107-127: P3 text, no gamma, top row first; returns bytes written or < 0 */

@@ -58,6 +58,7 @@ RENDER_RAW_SUM = 1
 RENDER_PREDICTORS = 2
 RENDER_COUNT_NODES = 4
 RENDER_PROFILE = 8
+RENDER_KEEP_PREDICTORS = 16
 SHARD_SAMPLES = 0
 SHARD_TILES = 1
 
@@ -176,6 +177,8 @@ def load_library() -> C.CDLL:
     lib.shim_tile_layout.argtypes = [_I, _I, _I, _I, _P, _I]
     lib.shim_camera_fields.restype = _I
     lib.shim_camera_fields.argtypes = [C.POINTER(Camera), _P]
+    lib.shim_aabb_hit.restype = _I
+    lib.shim_aabb_hit.argtypes = [_P, _P, _P, _P, _F, _F, _I]
     lib.shim_hrpp_hash.restype = C.c_uint64
     lib.shim_hrpp_hash.argtypes = [_P, _P]
     lib.shim_host_alloc.restype = _P

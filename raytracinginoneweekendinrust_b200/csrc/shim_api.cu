@@ -84,17 +84,16 @@ struct DeviceScene {
     int sm_count = 0;
     unsigned char* base = nullptr;
     SceneView view;
-    unsigned long long* hrpp_keys = nullptr;  // n_predictors x slots
-    uint32_t* hrpp_leaves = nullptr;           // n_predictors x slots x HRPP_LEAVES
+    HrppSlot* hrpp_slots = nullptr;            // n_predictors x slots
     size_t hrpp_slots_total = 0;
+    bool hrpp_cleared = false;                 // the tables hold what earlier renders learnt (SHIM_RENDER_KEEP_PREDICTORS)
     void release() {
-        if (!base && !hrpp_keys && !hrpp_leaves) return;
+        if (!base && !hrpp_slots) return;
         DeviceGuard g;
         if (g.enter(device) != cudaSuccess) return;
         if (base) cudaFree(base);
-        if (hrpp_keys) cudaFree(hrpp_keys);
-        if (hrpp_leaves) cudaFree(hrpp_leaves);
-        base = nullptr; hrpp_keys = nullptr; hrpp_leaves = nullptr; hrpp_slots_total = 0;
+        if (hrpp_slots) cudaFree(hrpp_slots);
+        base = nullptr; hrpp_slots = nullptr; hrpp_slots_total = 0;
     }
 };
 
@@ -210,10 +209,9 @@ static int upload_scene(shim::DeviceState* st, int device, DeviceScene** out) {
     if (st->n_predictors > 0) {  // one open-addressing table per predictor (cleared at the start of every render that uses them)
         const int log2 = st->hrpp_log2;
         d->hrpp_slots_total = ((size_t)1 << log2) * (size_t)st->n_predictors;
-        cudaError_t e1 = cudaMalloc(&d->hrpp_keys, d->hrpp_slots_total * sizeof(unsigned long long));
-        cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&d->hrpp_leaves, d->hrpp_slots_total * HRPP_LEAVES * sizeof(uint32_t)) : e1;
+        cudaError_t e2 = cudaMalloc(&d->hrpp_slots, d->hrpp_slots_total * sizeof(HrppSlot));
         if (e2 != cudaSuccess) { d->release(); return set_err(SHIM_ERR_CUDA, std::string("predictor tables: ") + cudaGetErrorString(e2)); }
-        v.hrpp_keys = d->hrpp_keys; v.hrpp_leaves = d->hrpp_leaves; v.hrpp_mask = (uint32_t)(((size_t)1 << log2) - 1); v.hrpp_log2 = log2;
+        v.hrpp_slots = d->hrpp_slots; v.hrpp_mask = (uint32_t)(((size_t)1 << log2) - 1); v.hrpp_log2 = log2;
     }
     *out = d.get();
     st->on[device] = std::move(d);
@@ -602,9 +600,10 @@ static int render_locked(shim_scene* s, DeviceScene& ds, Wavefront& w, const shi
     k.bg[0] = p.background[0]; k.bg[1] = p.background[1]; k.bg[2] = p.background[2];
     k.seed = p.seed; k.has_media = s->has_media ? 1 : 0; k.count_nodes = (p.flags & SHIM_RENDER_COUNT_NODES) ? 1 : 0;
     k.use_hrpp = ((p.flags & SHIM_RENDER_PREDICTORS) && s->dev->n_predictors > 0) ? 1 : 0;
-    if (k.use_hrpp) {  // a fresh Predictor per render (bvh.rs:69-81 builds them with the scene)
-        CU(cudaMemsetAsync(ds.hrpp_keys, 0, ds.hrpp_slots_total * sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(ds.hrpp_leaves, 0xFF, ds.hrpp_slots_total * HRPP_LEAVES * sizeof(uint32_t), st));
+    if (k.use_hrpp && !((p.flags & SHIM_RENDER_KEEP_PREDICTORS) && ds.hrpp_cleared)) {
+        // a fresh Predictor per render (bvh.rs:69-81 builds them with the scene) unless the caller keeps them
+        CU(cudaMemsetAsync(ds.hrpp_slots, 0xFF, ds.hrpp_slots_total * sizeof(HrppSlot), st));
+        ds.hrpp_cleared = true;
     }
     bool use_smem = false;
     choose_variant(s, s->dev, w, sw, k, &use_smem);

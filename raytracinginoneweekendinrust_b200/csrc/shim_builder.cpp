@@ -224,6 +224,23 @@ SHIM_API int shim_camera_fields(const shim_camera* cam, float* out) {
     out[18] = c.lens_radius; out[19] = c.time0; out[20] = c.time1;
     return SHIM_OK;
 }
+SHIM_API int shim_aabb_hit(const float* mn, const float* mx, const float* o, const float* d, float t_min, float t_max, int layout) {
+    if (!mn || !mx || !o || !d) return set_err(SHIM_ERR_INVALID, "shim_aabb_hit: null argument");
+    Ray r; r.o = mk3(o[0], o[1], o[2]); r.d = mk3(d[0], d[1], d[2]); r.time = 0;
+    RayCtx c;
+    make_ctx(c, r);
+    float t_near;
+    if (layout == 0) return slab(mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], c, t_min, t_max, t_near) ? 1 : 0;
+    // signed layout: the box as both children of an SNode, the ray picks the plane order by its direction signs
+    f4 q[3];
+    for (int k = 0; k < 3; ++k) {
+        const bool neg = (c.soff[k] & 16) != 0;
+        q[k] = neg ? f4{mx[k], mx[k], mn[k], mn[k]} : f4{mn[k], mn[k], mx[k], mx[k]};
+    }
+    float tl, tr; bool hl, hr;
+    slab_pair_signed(q[0], q[1], q[2], c, t_min, t_max, tl, tr, hl, hr);
+    return (hl && hr) ? 1 : ((hl || hr) ? set_err(SHIM_ERR_STATE, "shim_aabb_hit: the two children of one box disagree") : 0);
+}
 SHIM_API uint64_t shim_hrpp_hash(const float* o, const float* d) {
     Ray r; r.o = mk3(o[0], o[1], o[2]); r.d = mk3(d[0], d[1], d[2]); r.time = 0;
     return hrpp_hash(r);

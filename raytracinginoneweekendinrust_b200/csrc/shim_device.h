@@ -377,6 +377,17 @@ SHIM_HD bool tie_goes_to_candidate(const SceneView& sv, const RayCtx& c, float t
 #define SHIM_STACK_END 0x7fffffff
 SHIM_HD float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }   // FMNMX3 on sm_100a
 SHIM_HD float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// Both child boxes of an SNode against one ray: X, Y, Z are the ray's {near_l, near_r, far_l, far_r} plane quadruples
+// (SNode::ax[2 * axis + sign]); same result as two slab() calls on the plain node.
+SHIM_HD void slab_pair_signed(const f4& X, const f4& Y, const f4& Z, const RayCtx& c, float t_min, float t_cull, float& tl, float& tr,
+                              bool& hl, bool& hr) {
+    tl = fmaxf(max3f(slab_plane(X.x, c.inv_d.x, c.o_inv.x), slab_plane(Y.x, c.inv_d.y, c.o_inv.y), slab_plane(Z.x, c.inv_d.z, c.o_inv.z)), t_min);
+    tr = fmaxf(max3f(slab_plane(X.y, c.inv_d.x, c.o_inv.x), slab_plane(Y.y, c.inv_d.y, c.o_inv.y), slab_plane(Z.y, c.inv_d.z, c.o_inv.z)), t_min);
+    const float fl = fminf(min3f(slab_plane(X.z, c.inv_d.x, c.o_inv.x), slab_plane(Y.z, c.inv_d.y, c.o_inv.y), slab_plane(Z.z, c.inv_d.z, c.o_inv.z)), t_cull);
+    const float fr = fminf(min3f(slab_plane(X.w, c.inv_d.x, c.o_inv.x), slab_plane(Y.w, c.inv_d.y, c.o_inv.y), slab_plane(Z.w, c.inv_d.z, c.o_inv.z)), t_cull);
+    hl = !(fl < tl);   // aabb.rs:36 rejects only when t_max < t_min
+    hr = !(fr < tr);
+}
 // SIGNED: walk sv.snodes (SNode, see shim_types.h); start_node and every non-negative reference are then byte offsets.
 // Both layouts visit the same nodes in the same order and return the same hit: for a box with min <= max and a finite
 // reciprocal the plane the sign picks IS the smaller of the two products (fma is monotonic), and max/min are
@@ -424,12 +435,8 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
                 Z = *reinterpret_cast<const f4*>(nb + c.soff[2]);
                 nd = *reinterpret_cast<const i4*>(nb + 96);
 #endif
-                tl = fmaxf(max3f(slab_plane(X.x, c.inv_d.x, c.o_inv.x), slab_plane(Y.x, c.inv_d.y, c.o_inv.y), slab_plane(Z.x, c.inv_d.z, c.o_inv.z)), t_min);
-                tr = fmaxf(max3f(slab_plane(X.y, c.inv_d.x, c.o_inv.x), slab_plane(Y.y, c.inv_d.y, c.o_inv.y), slab_plane(Z.y, c.inv_d.z, c.o_inv.z)), t_min);
-                const float fl = fminf(min3f(slab_plane(X.z, c.inv_d.x, c.o_inv.x), slab_plane(Y.z, c.inv_d.y, c.o_inv.y), slab_plane(Z.z, c.inv_d.z, c.o_inv.z)), t_cull);
-                const float fr = fminf(min3f(slab_plane(X.w, c.inv_d.x, c.o_inv.x), slab_plane(Y.w, c.inv_d.y, c.o_inv.y), slab_plane(Z.w, c.inv_d.z, c.o_inv.z)), t_cull);
-                hl = !(fl < tl);
-                hr = !(fr < tr) && nd.y != CHILD_NONE;
+                slab_pair_signed(X, Y, Z, c, t_min, t_cull, tl, tr, hl, hr);
+                hr = hr && nd.y != CHILD_NONE;
                 left = nd.x; right = nd.y;
             } else {
                 const DevNode& n = sv.nodes[cur];
@@ -553,35 +560,51 @@ SHIM_HD size_t hrpp_home(const SceneView& sv, int table, unsigned long long key)
     unsigned long long h = (key * 0x9E3779B97F4A7C15ull) >> (64 - sv.hrpp_log2);
     return (size_t)table * ((size_t)sv.hrpp_mask + 1) + (size_t)h;
 }
-// Predictor::get_predictions, hrpp.rs:59-62: slot index or -1
-SHIM_HD long long hrpp_lookup(const SceneView& sv, int table, unsigned long long key) {
+#define SHIM_HRPP_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+// One probe of the neighbourhood serves the lookup (Predictor::get_predictions, hrpp.rs:59-62) and, after a miss,
+// the insert (Predictor::insert, hrpp.rs:64-82): `found` = the slot that holds the key, `empty` = the first empty
+// slot before the end of the probe sequence (where the key would be inserted), -1 = none.  All HRPP_PROBES keys are
+// fetched before any is looked at, so a lookup costs one memory latency, not one per probe (a full table of other
+// rays' keys - the steady state of a render - made every miss a chain of eight dependent loads).
+struct HrppProbe { long long found, empty; };
+SHIM_HD HrppProbe hrpp_probe(const SceneView& sv, int table, unsigned long long key) {
     const unsigned long long tag = key | (1ull << 63);
-    size_t base = (size_t)table * ((size_t)sv.hrpp_mask + 1), home = hrpp_home(sv, table, key) - base;
+    const size_t base = (size_t)table * ((size_t)sv.hrpp_mask + 1), home = hrpp_home(sv, table, key) - base;
+    unsigned long long k[HRPP_PROBES];
+#pragma unroll
+    for (int p = 0; p < HRPP_PROBES; ++p) k[p] = sv.hrpp_slots[base + ((home + (size_t)p) & sv.hrpp_mask)].key;
+    HrppProbe r; r.found = -1; r.empty = -1;
+#pragma unroll
     for (int p = 0; p < HRPP_PROBES; ++p) {
-        size_t slot = base + ((home + (size_t)p) & sv.hrpp_mask);
-        unsigned long long k = sv.hrpp_keys[slot];
-        if (k == tag) return (long long)slot;
-        if (k == 0ull) return -1;
-    }
-    return -1;
-}
-// Predictor::insert, hrpp.rs:64-82
-SHIM_HD void hrpp_insert(const SceneView& sv, int table, unsigned long long key, uint32_t leaf) {
-    const unsigned long long tag = key | (1ull << 63);
-    size_t base = (size_t)table * ((size_t)sv.hrpp_mask + 1), home = hrpp_home(sv, table, key) - base;
-    for (int p = 0; p < HRPP_PROBES; ++p) {
-        size_t slot = base + ((home + (size_t)p) & sv.hrpp_mask);
-        unsigned long long k = sv.hrpp_keys[slot];
-        if (k == 0ull) k = hrpp_cas64(sv.hrpp_keys + slot, 0ull, tag), k = (k == 0ull) ? tag : k;
-        if (k != tag) continue;
-        uint32_t* l = sv.hrpp_leaves + slot * HRPP_LEAVES;
-        for (int j = 0; j < HRPP_LEAVES; ++j) {
-            uint32_t v = l[j];
-            if (v == SHIM_HRPP_EMPTY) v = hrpp_cas32(l + j, SHIM_HRPP_EMPTY, leaf), v = (v == SHIM_HRPP_EMPTY) ? leaf : v;
-            if (v == leaf) return;
+        if (r.found < 0 && r.empty < 0) {
+            if (k[p] == tag) r.found = (long long)(base + ((home + (size_t)p) & sv.hrpp_mask));
+            else if (k[p] == SHIM_HRPP_EMPTY_KEY) r.empty = (long long)(base + ((home + (size_t)p) & sv.hrpp_mask));
         }
-        return;  // the slot's leaf list is full
     }
+    return r;
+}
+// adds `leaf` to the predictions of `slot` (which holds the ray's key); a full leaf list drops it (the cap, hrpp.rs:65)
+SHIM_HD void hrpp_add_leaf(const SceneView& sv, long long slot, uint32_t leaf) {
+    uint32_t* l = sv.hrpp_slots[slot].leaf;
+    for (int j = 0; j < HRPP_LEAVES; ++j) {
+        uint32_t v = l[j];
+        if (v == SHIM_HRPP_EMPTY) v = hrpp_cas32(l + j, SHIM_HRPP_EMPTY, leaf), v = (v == SHIM_HRPP_EMPTY) ? leaf : v;
+        if (v == leaf) return;
+    }
+}
+// Predictor::insert after a probe: into the slot that holds the key, else claim the empty slot the probe saw (if another
+// ray claimed it for another key in the meantime the prediction is dropped - the table is a cache); a neighbourhood
+// without an empty slot drops it too
+SHIM_HD void hrpp_insert(const SceneView& sv, const HrppProbe& pr, unsigned long long key, uint32_t leaf) {
+    long long slot = pr.found;
+    if (slot < 0) {
+        if (pr.empty < 0) return;
+        const unsigned long long tag = key | (1ull << 63);
+        const unsigned long long old = hrpp_cas64(&sv.hrpp_slots[pr.empty].key, SHIM_HRPP_EMPTY_KEY, tag);
+        if (old != SHIM_HRPP_EMPTY_KEY && old != tag) return;
+        slot = pr.empty;
+    }
+    hrpp_add_leaf(sv, slot, leaf);
 }
 
 // Bvh::hit with a predictor, bvh.rs:107-211 (GO_UP_LEVEL = 0: predictions are leaf nodes).  A hit found in the
@@ -590,12 +613,12 @@ template <bool COUNT>
 SHIM_HD bool bvh_closest_predicted(const SceneView& sv, const DevObject& ob, const RayCtx& c, float t_min, float t_max, BvhBest& best,
                                    TraceCounters* cnt) {
     const unsigned long long key = hrpp_hash(c.r);
-    long long slot = hrpp_lookup(sv, ob.predictor, key);
-    if (slot >= 0) {
+    const HrppProbe pr = hrpp_probe(sv, ob.predictor, key);
+    if (pr.found >= 0) {
         float closest = t_max;
         bool any = false;
         for (int j = 0; j < HRPP_LEAVES; ++j) {
-            uint32_t node = sv.hrpp_leaves[(size_t)slot * HRPP_LEAVES + j];
+            uint32_t node = sv.hrpp_slots[pr.found].leaf[j];
             if (node == SHIM_HRPP_EMPTY) break;
             BvhBest b;
             if (bvh_closest<COUNT>(sv, (int)node, c, t_min, closest, b, cnt)) { closest = b.t; best = b; any = true; }
@@ -607,7 +630,7 @@ SHIM_HD bool bvh_closest_predicted(const SceneView& sv, const DevObject& ob, con
     }
     if (!bvh_closest<COUNT>(sv, ob.ref, c, t_min, t_max, best, cnt)) return false;
     int leaf = table_of(sv.leaf, prim_type(best.prim))[prim_index(best.prim)];
-    hrpp_insert(sv, ob.predictor, key, (uint32_t)leaf);
+    hrpp_insert(sv, pr, key, (uint32_t)leaf);
     return true;
 }
 

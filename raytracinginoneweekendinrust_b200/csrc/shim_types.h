@@ -88,6 +88,7 @@ struct alignas(16) DevObject {
     int n_nodes, pad0, pad1, pad2;
 };
 
+struct HrppSlot;
 struct SceneView {
     const DevNode* nodes;
     const SNode* snodes;    // the nodes again in the signed layout, or null (built for scenes that fit shared memory)
@@ -110,13 +111,20 @@ struct SceneView {
     int n_objects;
     int n_nodes;
     // HRPP predictor tables (hrpp.rs:33-83), one per BVH that carries a predictor: open addressing,
-    // hrpp_mask + 1 slots each; a slot = tagged 48-bit key + up to HRPP_LEAVES predicted leaf nodes
-    unsigned long long* hrpp_keys;
-    uint32_t* hrpp_leaves;
+    // hrpp_mask + 1 slots each
+    struct HrppSlot* hrpp_slots;
     uint32_t hrpp_mask;
     int hrpp_log2;
 };
 enum { HRPP_LEAVES = 4, HRPP_PROBES = 8 };
+// One predictor slot = one 32-byte sector: the tagged 48-bit key and up to HRPP_LEAVES predicted leaf nodes, so a
+// lookup that hits costs one memory transaction.  Empty = all ones (a table is cleared with one memset of 0xFF;
+// a tag has bit 63 set and bits 48-62 clear, so it is never all ones).
+struct alignas(32) HrppSlot {
+    unsigned long long key;
+    uint32_t leaf[HRPP_LEAVES];
+    uint32_t pad[2];
+};
 
 struct CameraPod {  // camera.rs:6-27, derived on the host by Camera::new
     f3 origin, horizontal, vertical, llc, u, v;

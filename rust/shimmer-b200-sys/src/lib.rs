@@ -24,6 +24,7 @@ pub const SHIM_RENDER_RAW_SUM: i32 = 1;
 pub const SHIM_RENDER_PREDICTORS: i32 = 2;
 pub const SHIM_RENDER_COUNT_NODES: i32 = 4;
 pub const SHIM_RENDER_PROFILE: i32 = 8;
+pub const SHIM_RENDER_KEEP_PREDICTORS: i32 = 16;
 
 pub const SHIM_SHARD_SAMPLES: c_int = 0;
 pub const SHIM_SHARD_TILES: c_int = 1;
@@ -162,6 +163,9 @@ extern "C" {
 
     pub fn shim_tile_layout(image_width: c_int, image_height: c_int, tile_width: c_int, tile_height: c_int, out4: *mut i32, cap: c_int) -> c_int;
     pub fn shim_camera_fields(cam: *const shim_camera, out21: *mut f32) -> c_int;
+    pub fn shim_aabb_hit(
+        min3: *const f32, max3: *const f32, origin3: *const f32, direction3: *const f32, t_min: f32, t_max: f32, layout: c_int,
+    ) -> c_int;
     pub fn shim_hrpp_hash(origin3: *const f32, direction3: *const f32) -> u64;
     pub fn shim_write_ppm(rgb: *const f32, width: c_int, height: c_int, path: *const c_char) -> i64;
 }

@@ -19,13 +19,13 @@ void shim::device_state_release(DeviceState*) {}
 // HRPP tables of the harness (the product keeps them in device memory)
 #include <map>
 namespace {
-struct HrppHost { std::vector<unsigned long long> keys; std::vector<uint32_t> leaves; int log2 = 0; bool on = false; uint64_t tp = 0, fp = 0, none = 0; };
+struct HrppHost { std::vector<HrppSlot> slots; int log2 = 0; bool on = false; uint64_t tp = 0, fp = 0, none = 0; };
 std::map<shim_scene*, HrppHost> g_hrpp;
 SceneView view_of(shim_scene* s) {
     SceneView sv = s->flat.view();
     auto it = g_hrpp.find(s);
     if (it != g_hrpp.end() && it->second.on) {
-        sv.hrpp_keys = it->second.keys.data(); sv.hrpp_leaves = it->second.leaves.data();
+        sv.hrpp_slots = it->second.slots.data();
         sv.hrpp_log2 = it->second.log2; sv.hrpp_mask = (uint32_t)(((size_t)1 << it->second.log2) - 1);
     }
     return sv;
@@ -42,8 +42,9 @@ extern "C" __attribute__((visibility("default"))) int hs_enable_predictors(shim_
     HrppHost& h = g_hrpp[s];
     size_t n = s->flat.predictor_bvh.size();
     h.log2 = log2; h.on = n > 0; h.tp = h.fp = h.none = 0;
-    h.keys.assign(((size_t)1 << log2) * n, 0ull);
-    h.leaves.assign(((size_t)1 << log2) * n * HRPP_LEAVES, 0xFFFFFFFFu);
+    HrppSlot empty;
+    memset(&empty, 0xFF, sizeof empty);
+    h.slots.assign(((size_t)1 << log2) * n, empty);
     return (int)n;
 }
 extern "C" __attribute__((visibility("default"))) void hs_predictor_stats(shim_scene* s, uint64_t* out3) {

@@ -48,3 +48,48 @@ def test_gate2_converged_image_4096spp(name, size):
     assert rmse <= 1e-3
     assert outliers <= max(1, W * H // 100)
     assert abs(int(st.rays) - int(so.rays)) <= so.rays // 1000 + 16
+
+
+def test_reference_aabb_vectors_on_the_device():
+    """aabb.rs:74-97 (`hits`, `misses`) through the DEVICE box test: each reference box is the bounding box of a cube
+    that sits in a Bvh next to a far-away cube, the reference ray (origin 0, direction +z, i.e. zero x / y components,
+    t in [0, 5]) is traced with shim_trace_closest.  A ray that hits the box hits the cube's front face at the box's
+    entry distance, a ray that misses the box reports no primitive.  A sweep of zero-component rays follows."""
+    import numpy as np
+    from raytracinginoneweekendinrust_b200 import api
+    ids = {}
+    for name, (mn, mx) in {"hits": ((-1, -1, 1), (1, 1, 2)), "misses": ((1, 1, 1), (2, 2, 2))}.items():
+        got = {}
+        for side, s in (("gpu", api.Scene()), ("oracle", support.OracleScene())):
+            m = s.lambertian_color(0.5, 0.5, 0.5)
+            lst = s.list_create()
+            box = s.cube(mn, mx, m)
+            s.list_add(lst, box)
+            s.list_add(lst, s.cube((50, 50, 50), (51, 51, 51), m))
+            s.world_add(s.bvh(lst, seed=1))
+            s.commit()
+            ray = np.array([[0, 0, 0, 0, 0, 1, 0]], np.float32)
+            p, t = s.trace_closest(ray, t_min=0.0, t_max=5.0)
+            got[side] = (int(p[0]), float(t[0]), box)
+        ids[name] = got
+        assert got["gpu"][:2] == got["oracle"][:2], (name, got)
+    assert ids["hits"]["gpu"][0] == ids["hits"]["gpu"][2] and ids["hits"]["gpu"][1] == 1.0
+    assert ids["misses"]["gpu"][0] == -1
+    # zero-component and axis-parallel rays against a whole scene, both sides
+    g, o, info = T.build_pair("random-spheres")
+    rs = np.random.RandomState(11)
+    n = 20000
+    rays = np.zeros((n, 7), np.float32)
+    rays[:, 0:3] = rs.uniform(-12, 12, (n, 3)); rays[:, 1] = rs.uniform(0.05, 3, n)
+    rays[:, 3:6] = rs.uniform(-1, 1, (n, 3))
+    for i in range(n):
+        k = rs.randint(0, 3)
+        rays[i, 3 + k] = [0.0, -0.0][rs.randint(0, 2)]
+        if rs.rand() < 0.4:
+            rays[i, 3 + (k + 1) % 3] = [0.0, -0.0][rs.randint(0, 2)]
+    p_ref, t_ref = o.trace_closest(rays)
+    p_gpu, t_gpu = g.trace_closest(rays)
+    assert (p_ref != p_gpu).sum() == 0
+    hit = p_ref >= 0
+    assert hit.sum() > 1000
+    np.testing.assert_array_equal(t_ref[hit].view(np.uint32), t_gpu[hit].view(np.uint32))

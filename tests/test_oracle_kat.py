@@ -23,6 +23,46 @@ def test_aabb_hits_and_misses(orc):
     assert orc.orc_aabb_hit(mn.ctypes.data, mx.ctypes.data, o.ctypes.data, d.ctypes.data, 0.0, 5.0) == 0
 
 
+@pytest.mark.parametrize("layout", [0, 1])
+def test_aabb_hits_and_misses_through_the_products_slab(orc, layout):
+    """The reference's two `Aabb::hit` vectors (aabb.rs:74-97; both rays have zero x/y direction components, i.e.
+    1/0 = inf in the reference) through the PRODUCT's box test - the plain node's slab and the signed node's - and a
+    seeded sweep of boxes against axis-parallel, zero-component (+0 and -0) and general rays where oracle and product
+    must agree.  Rays that graze a box face exactly are left out: there the reference compares (plane - o) * (1/d)
+    against t, the product fma(plane, 1/d, -o/d), which may differ in the last ulp."""
+    from raytracinginoneweekendinrust_b200 import capi
+    lib = capi.load_library()
+
+    def prod(mn, mx, o, d, t0, t1):
+        return lib.shim_aabb_hit(mn.ctypes.data, mx.ctypes.data, o.ctypes.data, d.ctypes.data, t0, t1, layout)
+
+    o, d = f3(0, 0, 0), f3(0, 0, 1)
+    assert prod(f3(-1, -1, 1), f3(1, 1, 2), o, d, 0.0, 5.0) == 1          # aabb.rs `hits`
+    assert prod(f3(1, 1, 1), f3(2, 2, 2), o, d, 0.0, 5.0) == 0            # aabb.rs `misses`
+    rs = np.random.RandomState(5)
+    checked = 0
+    for i in range(4000):
+        mn = rs.uniform(-4, 3, 3).astype(np.float32)
+        mx = (mn + rs.uniform(0.1, 3, 3)).astype(np.float32)
+        o = rs.uniform(-6, 6, 3).astype(np.float32)
+        d = rs.uniform(-1, 1, 3).astype(np.float32)
+        for k in range(3):
+            u = rs.rand()
+            if u < 0.25:
+                d[k] = np.float32(0.0) if rs.rand() < 0.5 else np.float32(-0.0)
+        if not d.any():
+            d[rs.randint(0, 3)] = 1.0
+        t0, t1 = 0.001, float(rs.choice([5.0, 50.0, np.inf]))
+        # skip exact grazes: an origin coordinate on a box plane with a zero direction component (0 * inf = NaN in
+        # the reference makes the outcome depend on NaN comparison order)
+        if any(d[k] == 0 and (o[k] == mn[k] or o[k] == mx[k]) for k in range(3)):
+            continue
+        want = orc.orc_aabb_hit(mn.ctypes.data, mx.ctypes.data, o.ctypes.data, d.ctypes.data, t0, t1)
+        assert prod(mn, mx, o, d, t0, t1) == want, (mn, mx, o, d, t0, t1)
+        checked += 1
+    assert checked > 3900
+
+
 # ---- aabb.rs test `union` ------------------------------------------------------------------------
 def test_aabb_union(orc):
     a = np.array([0, 1, 0, 2, 4, 2], np.float32)

@@ -72,3 +72,32 @@ def test_library_exports_what_the_rust_crate_links_against():
     lib = capi.load_library()
     for name in _rust_functions():
         assert hasattr(lib, name), name
+
+
+def test_reference_patch_applies_cleanly(tmp_path):
+    """rust/shimmer-patch/shimmer-b200.patch (the `record` method of every implementor, Bvh upload, Camera POD, the new
+    body of Renderer::render, src/backend.rs) applies to a pristine copy of the reference crate and is what
+    make_patch.py generates from it.  No Rust toolchain exists in this image: applying is all that can be checked."""
+    import shutil
+    import subprocess
+    import pytest
+    ref = Path("/root/reference")
+    if not (ref / "src" / "renderer.rs").exists() or shutil.which("patch") is None:
+        pytest.skip("needs the reference checkout and patch(1)")
+    patch = ROOT / "rust" / "shimmer-patch" / "shimmer-b200.patch"
+    work = tmp_path / "shimmer"
+    work.mkdir()
+    shutil.copy(ref / "Cargo.toml", work / "Cargo.toml")
+    shutil.copytree(ref / "src", work / "src")
+    out = subprocess.run(["patch", "-p1", "--no-backup-if-mismatch", "-i", str(patch)], cwd=work, capture_output=True, text=True)
+    assert out.returncode == 0 and "FAILED" not in out.stdout and "fuzz" not in out.stdout, out.stdout + out.stderr
+    assert (work / "src" / "backend.rs").read_text() == (ROOT / "rust" / "shimmer-patch" / "backend.rs").read_text()
+    # every implementor the crate ships overrides `record`: 4 textures, 5 materials, 12 hittables
+    n = sum(p.read_text().count("fn record(&self, r: &mut crate::backend::Recorder)") for p in (work / "src").rglob("*.rs"))
+    assert n == 4 + 5 + 12, n
+    assert "crate::backend::render_on_device(" in (work / "src" / "renderer.rs").read_text()
+    # the committed patch is what the generator produces today
+    before = patch.read_text()
+    gen = subprocess.run(["python", str(ROOT / "rust" / "shimmer-patch" / "make_patch.py"), str(ref)], capture_output=True, text=True)
+    assert gen.returncode == 0, gen.stderr
+    assert patch.read_text() == before
