@@ -142,7 +142,7 @@ typedef struct shim_stats {
     double device_ms;              /* CUDA events around the wavefront loop */
     double extend_ms, shade_ms, generate_ms; /* event sums per kernel class (extend only, with SHIM_RENDER_PROFILE) */
     uint64_t extend_launches;      /* wf_extend launches that had rays, covered by extend_ms */
-    uint64_t extend_variant;       /* which closest-hit kernel ran: 0 wf_extend, 1 wf_extend_bvh1, 2 wf_extend_solo, 3 wf_extend_list, 4 wf_trace_solo */
+    uint64_t extend_variant;       /* which closest-hit kernel ran: 0 wf_extend, 1 wf_bvh1_list + wf_bvh1_walk + wf_bvh1_finish, 2 wf_extend_solo, 3 wf_extend_list, 4 wf_trace_solo */
     uint64_t pool_paths;           /* paths in flight this render was given (min(samples, 2^24) unless pool_paths says otherwise) */
     uint64_t pool_bytes;           /* device memory of the wavefront pool(s) after this render (queues, counters, framebuffers) */
     uint64_t devices;              /* devices that rendered (1 except for shim_render_multi) */

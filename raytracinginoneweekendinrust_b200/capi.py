@@ -82,7 +82,7 @@ class Stats(C.Structure):
         ("wall_ms", C.c_double),
     ]
 
-    EXTEND_KERNELS = {0: "wf_extend", 1: "wf_extend_bvh1", 2: "wf_extend_solo", 3: "wf_extend_list", 4: "wf_trace_solo"}
+    EXTEND_KERNELS = {0: "wf_extend", 1: "wf_bvh1_walk", 2: "wf_extend_solo", 3: "wf_extend_list", 4: "wf_trace_solo"}
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -106,6 +106,8 @@ struct Wavefront {
     int device = -1, sm_count = 0, max_smem = 0;
     DevBuf<f4> ray_o[2], ray_d[2], thr[2];         // ray queues: wavefront pipeline only
     DevBuf<f4> mq_o, mq_d, mq_thr, mq_hit;          // material queues (sets x regions x pool entries)
+    DevBuf<i4> bvh1_hit;                            // one-Bvh worlds: hit record per queued ray
+    DevBuf<uint32_t> bvh1_queue;                    // ... and the rays that can reach the tree
     DevBuf<uint32_t> cnt;
     DevBuf<float> accum, d_out, d_peer;
     float* h_out = nullptr;  // pinned staging for a pageable host framebuffer
@@ -115,7 +117,7 @@ struct Wavefront {
     uint32_t npix = 0;
     uint32_t* h_flags = nullptr;  // pinned: done flag / counter readbacks
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr};
-    int grid_extend_gmem = 0, grid_extend_gmem_bvh1 = 0, grid_shade = 0, grid_generate = 0, grid_tail = 0;
+    int grid_extend_gmem = 0, grid_bvh1_walk = 0, grid_stream = 0, grid_shade = 0, grid_generate = 0, grid_tail = 0;
     cudaStream_t capture_stream = nullptr;         // graphs are captured here (the caller's stream may be the legacy default stream)
     cudaStream_t work_stream = nullptr;            // shim_render_multi renders on it
     struct LoopGraph { cudaGraphExec_t exec; unsigned long long handle; };
@@ -124,14 +126,14 @@ struct Wavefront {
     std::vector<cudaEvent_t> prof;                 // event pairs around the launches of an iteration (SHIM_RENDER_PROFILE)
     std::vector<cudaEvent_t> ev_d2h;
     size_t pool_bytes() const {
-        size_t b = mq_o.bytes() + mq_d.bytes() + mq_thr.bytes() + mq_hit.bytes() + cnt.bytes() + accum.bytes() + d_out.bytes() + d_peer.bytes() +
+        size_t b = bvh1_hit.bytes() + bvh1_queue.bytes() + mq_o.bytes() + mq_d.bytes() + mq_thr.bytes() + mq_hit.bytes() + cnt.bytes() + accum.bytes() + d_out.bytes() + d_peer.bytes() +
                    pix_table.bytes();
         for (int i = 0; i < 2; ++i) b += ray_o[i].bytes() + ray_d[i].bytes() + thr[i].bytes();
         return b;
     }
     void release() {   // with the device current
         for (int i = 0; i < 2; ++i) { ray_o[i].release(); ray_d[i].release(); thr[i].release(); }
-        mq_o.release(); mq_d.release(); mq_thr.release(); mq_hit.release(); cnt.release(); accum.release(); pix_table.release();
+        mq_o.release(); mq_d.release(); mq_thr.release(); mq_hit.release(); bvh1_hit.release(); bvh1_queue.release(); cnt.release(); accum.release(); pix_table.release();
         d_out.release(); d_peer.release();
         if (h_flags) cudaFreeHost(h_flags);
         if (h_out) cudaFreeHost(h_out);
@@ -325,10 +327,8 @@ static int wf_init(Wavefront& w, int device) {
     CU(opt_in_smem(wf_extend<true, false, false, false>, dyn)); CU(opt_in_smem(wf_extend<true, false, true, false>, dyn));
     CU(opt_in_smem(wf_extend<true, true, false, false>, dyn));  CU(opt_in_smem(wf_extend<true, true, true, false>, dyn));
     CU(opt_in_smem(wf_extend<true, false, false, true>, dyn));  CU(opt_in_smem(wf_extend<true, false, true, true>, dyn));
-    CU(opt_in_smem(wf_extend_bvh1<true, false>, dyn));  CU(opt_in_smem(wf_extend_bvh1<true, true>, dyn));
-    CU(opt_in_smem(wf_extend_bvh1<false, false>, dyn)); CU(opt_in_smem(wf_extend_bvh1<false, true>, dyn));
-    CU(opt_in_smem(wf_extend_bvh1<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI>, dyn));
-    CU(opt_in_smem(wf_extend_bvh1<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI>, dyn));
+    CU(opt_in_smem(wf_bvh1_walk<true, false>, dyn));  CU(opt_in_smem(wf_bvh1_walk<true, true>, dyn));
+    CU(opt_in_smem(wf_bvh1_walk<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI>, dyn));
     CU(opt_in_smem(wf_extend_list<false, SHIM_LIST_THREADS>, dyn)); CU(opt_in_smem(wf_extend_list<true, SHIM_LIST_THREADS>, dyn));
     CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, false>, dyn));
     CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, true>, dyn));
@@ -339,6 +339,10 @@ static int wf_init(Wavefront& w, int device) {
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_extend<false, false, false, false>, SHIM_EXTEND_THREADS, 0));
     w.grid_extend_gmem = w.sm_count * (per_sm > 0 ? per_sm : 1);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI>, SHIM_BVH1_TRI_THREADS, 0));
+    w.grid_bvh1_walk = w.sm_count * (per_sm > 0 ? per_sm : 1);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_bvh1_finish, 256, 0));
+    w.grid_stream = w.sm_count * (per_sm > 0 ? per_sm : 1);
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_shade, 256, 0));
     w.grid_shade = w.sm_count * (per_sm > 0 ? per_sm : 1);
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_generate, 256, 0));
@@ -368,14 +372,13 @@ struct Switches {
 static void choose_variant(const shim_scene* s, const shim::DeviceState* st, const Wavefront& w, const Switches& sw, WfParams& k, bool* use_smem_out) {
     const FlatScene& f = s->flat;
     k.bvh1_index = -1;
-    {   // worlds with exactly one BVH among at least one plain object, no medium, no predictor -> wf_extend_bvh1
+    {   // worlds with exactly one BVH among at least one plain object, no medium, no predictor -> wf_bvh1_list / _walk / _finish
         int n_bvh = 0, idx = -1;
         for (size_t i = 0; i < f.objects.size(); ++i) if (f.objects[i].kind == OBJ_BVH) { ++n_bvh; idx = (int)i; }
         if (n_bvh == 1 && f.objects.size() > 1 && !s->has_media && !k.use_hrpp && !sw.no_bvh1) k.bvh1_index = idx;
     }
     k.smem = st->smem;
-    const int smem_extra = k.bvh1_index >= 0 ? SHIM_BVH1_SMEM_BYTES : 0;
-    const bool use_smem = k.smem.total != 0 && (int)k.smem.total + smem_extra <= w.max_smem - 1024 && !sw.no_smem;
+    const bool use_smem = k.smem.total != 0 && (int)k.smem.total <= w.max_smem - 1024 && !sw.no_smem;
     if (!use_smem) k.smem.total = 0;
     *use_smem_out = use_smem;
     k.solo = 0; k.solo_only = -1; k.fused_generate = 0; k.trace_pipeline = 0;
@@ -431,6 +434,8 @@ static int wf_reserve(Wavefront& w, const shim::DeviceState* st, const shim_rend
     CU(w.mq_o.reserve(mq_entries)); CU(w.mq_d.reserve(mq_entries)); CU(w.mq_thr.reserve(mq_entries)); CU(w.mq_hit.reserve(mq_entries));
     if (!k.trace_pipeline)   // ray queues belong to the wavefront pipeline
         for (int i = 0; i < 2; ++i) { CU(w.ray_o[i].reserve(pool)); CU(w.ray_d[i].reserve(pool)); CU(w.thr[i].reserve(pool)); }
+    if (k.bvh1_index >= 0) { CU(w.bvh1_hit.reserve(pool)); CU(w.bvh1_queue.reserve(pool)); }
+    k.bvh1_hit = w.bvh1_hit.p; k.bvh1_queue = w.bvh1_queue.p;
     for (int i = 0; i < 2; ++i) { k.ray_o[i] = w.ray_o[i].p; k.ray_d[i] = w.ray_d[i].p; k.thr[i] = w.thr[i].p; }
     k.mq_o = w.mq_o.p; k.mq_d = w.mq_d.p; k.mq_thr = w.mq_thr.p; k.mq_hit = w.mq_hit.p;
     return SHIM_OK;
@@ -440,16 +445,18 @@ static void launch_extend(const Wavefront& w, const WfParams& k, bool use_smem, 
     const int grid = use_smem ? w.sm_count : w.grid_extend_gmem;   // one persistent block per SM owns the shared-memory copy of the scene
     const uint32_t smem = use_smem ? k.smem.total : 0;
     const bool S = use_smem, C = k.count_nodes != 0, M = k.has_media != 0, H = k.use_hrpp != 0;
-    if (k.bvh1_index >= 0) {  // one BVH among plain objects, no medium, no predictor: two-phase variant
+    if (k.bvh1_index >= 0) {  // one BVH among plain objects, no medium, no predictor: list pass, dense tree walk, finish pass
+        if (C) wf_bvh1_list<true><<<w.grid_stream, 256, 0, st>>>(); else wf_bvh1_list<false><<<w.grid_stream, 256, 0, st>>>();
+        const int wgrid = S ? w.sm_count : w.grid_bvh1_walk;
         if (k.bvh1_tri_threads && !C) {   // triangle-only tree: no primitive dispatch, more warps
-            const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES_T(SHIM_BVH1_TRI_THREADS);
-            if (S) wf_extend_bvh1<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<grid, SHIM_BVH1_TRI_THREADS, dyn, st>>>();
-            else wf_extend_bvh1<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<grid, SHIM_BVH1_TRI_THREADS, dyn, st>>>();
-            return;
+            if (S) wf_bvh1_walk<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<wgrid, SHIM_BVH1_TRI_THREADS, smem, st>>>();
+            else wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<wgrid, SHIM_BVH1_TRI_THREADS, 0, st>>>();
+        } else if (S) {
+            if (C) wf_bvh1_walk<true, true><<<wgrid, SHIM_EXTEND_THREADS, smem, st>>>(); else wf_bvh1_walk<true, false><<<wgrid, SHIM_EXTEND_THREADS, smem, st>>>();
+        } else {
+            if (C) wf_bvh1_walk<false, true><<<wgrid, SHIM_EXTEND_THREADS, 0, st>>>(); else wf_bvh1_walk<false, false><<<wgrid, SHIM_EXTEND_THREADS, 0, st>>>();
         }
-        const uint32_t dyn = smem + SHIM_BVH1_SMEM_BYTES_T(SHIM_EXTEND_THREADS);
-        if (S) { if (C) wf_extend_bvh1<true, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<true, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
-        else   { if (C) wf_extend_bvh1<false, true><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); else wf_extend_bvh1<false, false><<<grid, SHIM_EXTEND_THREADS, dyn, st>>>(); }
+        wf_bvh1_finish<<<w.grid_stream, 256, 0, st>>>();
         return;
     }
     if (k.list_threads) {   // no Bvh in the world, scene image in shared memory
@@ -681,7 +688,8 @@ static int render_locked(shim_scene* s, DeviceScene& ds, Wavefront& w, const shi
         stats->extend_variant = k.trace_pipeline ? 4u : k.solo ? 2u : (k.list_threads ? 3u : (k.bvh1_index >= 0 ? 1u : 0u));
         // trace pipeline: wf_trace_first + two kernels per iteration body + wf_finalize; wavefront: four per body + wf_finalize
         // (the last body may find the queue already empty)
-        stats->kernel_launches = !run ? 1ull : (k.trace_pipeline ? 2ull * w.h_flags[32 + CNT_BODIES] + 2ull : 4ull * w.h_flags[32 + CNT_BODIES] + 1ull);
+        stats->kernel_launches = !run ? 1ull : (k.trace_pipeline ? 2ull * w.h_flags[32 + CNT_BODIES] + 2ull
+                                                                 : (k.bvh1_index >= 0 ? 6ull : 4ull) * w.h_flags[32 + CNT_BODIES] + 1ull);
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
         stats->device_ms = ms;

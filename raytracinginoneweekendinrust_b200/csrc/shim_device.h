@@ -479,50 +479,6 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
     return best.any;
 }
 
-// Resumable form of the same walk for wf_extend_bvh1 (lanes of a warp interleave walking with fetching new rays).
-// The short stack is a separate local array so that the scalars stay in registers.
-struct BvhWalk { BvhBest best; float t_cull; int cur; int sp; };
-SHIM_HD void bvh_walk_init(BvhWalk& w, int start_node, float t_max) {
-    w.best.t = t_max; w.best.prim = 0; w.best.face = 0; w.best.any = false;
-    w.t_cull = t_max; w.sp = 0; w.cur = start_node;
-}
-SHIM_HD bool bvh_walk_done(const BvhWalk& w) { return w.cur == SHIM_STACK_END; }
-// advances to and through the next primitive test (or to the end of the walk)
-template <bool COUNT, int ONLY = -1>
-SHIM_HD void bvh_walk_step(const SceneView& sv, BvhWalk& w, int* stack, const RayCtx& c, float t_min, TraceCounters* cnt) {
-    while (w.cur >= 0 && w.cur != SHIM_STACK_END) {
-        const DevNode& n = sv.nodes[w.cur];
-        f4 na = n.a, nb = n.b, nc = n.c;
-        i4 nd = n.d;
-        if (COUNT) cnt->nodes++;
-        float tl, tr;
-        bool hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, t_min, w.t_cull, tl);
-        bool hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, t_min, w.t_cull, tr);
-        hr = hr && nd.y != CHILD_NONE;
-        if (hl && hr) {
-            bool swap = tr < tl;
-            w.cur = swap ? nd.y : nd.x;
-            if (w.sp < SHIM_BVH_STACK) stack[w.sp++] = swap ? nd.x : nd.y;
-        } else if (hl) {
-            w.cur = nd.x;
-        } else if (hr) {
-            w.cur = nd.y;
-        } else {
-            w.cur = w.sp > 0 ? stack[--w.sp] : SHIM_STACK_END;
-        }
-    }
-    if (w.cur == SHIM_STACK_END) return;
-    uint32_t ref = ~(uint32_t)w.cur;
-    float t; int face = 0;
-    if (COUNT) cnt->prims++;
-    if (hit_prim<ONLY>(sv, ref, c, t_min, w.t_cull, t, face) && !(t > w.best.t)) {
-        bool take = !w.best.any || t < w.best.t;
-        if (!take) take = tie_goes_to_candidate<ONLY>(sv, c, t_min, ref, w.best.prim, t);
-        if (take) { w.best.t = t; w.best.prim = ref; w.best.face = face; w.best.any = true; w.t_cull = t + fabsf(t) * 3.8146973e-06f; }
-    }
-    w.cur = w.sp > 0 ? stack[--w.sp] : SHIM_STACK_END;
-}
-
 // ---------------------------------------------------------------------------- hrpp.rs:132-193
 SHIM_HD uint32_t hrpp_map_float(float v) {
     uint32_t bits = (uint32_t)f2i(v);

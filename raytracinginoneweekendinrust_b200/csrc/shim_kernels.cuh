@@ -16,7 +16,7 @@
 //                256-ray chunk of a queue is streamed (coalesced) through code specialised for
 //                that material: rebuild the HitRecord, emit, scatter, and append the continuing
 //                ray to the next ray queue (warp-ballot compaction, one atomic per warp)
-//                (wf_extend_solo / wf_extend_list / wf_extend_bvh1: the same walk with what a
+//                (wf_extend_solo / wf_extend_list: the same walk with what a
 //                scene cannot need compiled out - fewer registers, more resident warps;
 //                wf_trace_solo: shade + walk in one kernel, material queue to material queue)
 //   wf_tail      once no samples are left to start and at most 65536 paths are alive, one
@@ -34,6 +34,7 @@ namespace shim {
 
 enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..6 */, CNT_CUR = 7, CNT_TICKET = 8, CNT_NEXT_CUR = 9, CNT_DONE = 10, CNT_ITER = 11,
        CNT_BODIES = 12 /* iteration bodies executed */, CNT_GEN_BASE = 13 /* fused generation: queue slot of the first new sample */, CNT_U64_BASE = 14 /* u64 slots from here, as pairs */,
+       CNT_TREEQ = 30 /* one-Bvh worlds: rays queued for the tree walk */, CNT_TREEQ_NEXT = 31 /* ... handed out */,
        CNT_MQ1 = 32 /* ..36: second material-queue counter set (wf_trace pipeline) */, CNT_GEN_N = 37 /* new samples of this iteration */ };
 enum { C64_NEXT_SAMPLE = 0, C64_RAYS = 1, C64_NODES = 2, C64_PRIMS = 3, C64_HRPP_TP = 4, C64_HRPP_FP = 5, C64_HRPP_NONE = 6, C64_GEN_FIRST = 7, C64_COUNT = 8 };
 enum { CNT_WORDS = 40 };
@@ -72,13 +73,15 @@ struct WfParams {
     float bg[3];
     uint64_t seed;
     int has_media, count_nodes, use_hrpp;
-    int bvh1_tri_threads;   // > 0: the one Bvh holds only triangles: wf_extend_bvh1<.., THREADS, PT_TRI>
+    int bvh1_tri_threads;   // > 0: the one Bvh holds only triangles: wf_bvh1_walk<.., THREADS, PT_TRI>
     int list_threads; // > 0: the world has no Bvh: wf_extend_list with this many threads per block
     int trace_pipeline;   // the iteration is wf_trace (shade -> closest hit) + wf_tail_mq (endgame, loop condition, next counters); no ray queues
     int fused_generate;   // wf_generate only publishes the counters; wf_extend_solo makes the camera rays itself
     int solo_only;    // wf_extend_solo: the one primitive type of the Bvh (PT_*), or -1 when mixed
     int solo;         // > 0: the world is exactly one plain Bvh: wf_extend_solo with this many threads per block
-    int bvh1_index;   // >= 0: the world is one BVH object (this one) among plain primitives, no medium: wf_extend_bvh1 applies
+    int bvh1_index;   // >= 0: the world is one BVH object (this one) among plain primitives, no medium: the wf_bvh1_* kernels apply
+    i4* bvh1_hit;          // one-Bvh worlds: closest-hit record per queued ray (wf_bvh1_list / _walk / _finish)
+    uint32_t* bvh1_queue;  // ... rays that can reach the tree
     SmemLayout smem;
     unsigned long long loop_handle;   // conditional handle of the CUDA-graph WHILE node the iteration runs in (0: host-driven loop)
     uint32_t max_iterations;          // safety stop of the device-side loop
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(256) wf_generate() {
             c[1 - cur] = 0;
 #pragma unroll
             for (int k = 0; k < MAT_KINDS; ++k) c[CNT_MQ + k] = 0;
+            c[CNT_TREEQ] = 0; c[CNT_TREEQ_NEXT] = 0;
             *cnt64(c, C64_RAYS) += (unsigned long long)(n_cur + n);
             c[CNT_ITER] += (n_cur + n == 0) ? 0u : 1u;
             c[CNT_BODIES] += 1u;
@@ -323,7 +327,9 @@ __device__ __forceinline__ SceneView stage_scene(const WfParams& p, unsigned cha
 #endif
 #define SHIM_SOLO_ANY_THREADS 768      // one plain Bvh of mixed primitives: 80 registers
 #define SHIM_LIST_THREADS 1024         // worlds without a Bvh: 64 registers
+#ifndef SHIM_BVH1_TRI_THREADS
 #define SHIM_BVH1_TRI_THREADS 896      // one triangle-only Bvh among rects
+#endif
 template <bool SMEM, bool COUNT, bool MEDIA, bool HRPP>
 __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
     const WfParams& p = g_p;
@@ -367,180 +373,247 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_list() {
 // ---------------------------------------------------------------------------- extend, one-BVH worlds
 // Worlds like the reference's mesh scenes (main.rs:791-829): six Cornell rects + Translate(Bvh(triangles)).  Most
 // rays never enter the mesh's bounds, so in the plain kernel a warp idles on the few lanes that walk the tree
-// (measured 9 of 32 lanes active on the bunny config).  Here a warp takes 128 rays at a time.  Phase 1: every lane
-// tests the list objects and the BVH's root boxes for its ray; rays that cannot hit the tree are finished on the
-// spot, the others are compacted (warp ballot) into a shared-memory list.  Phase 2: the list is walked 32 entries
-// at a time, i.e. with dense warps.  List order is kept (hittable.rs:100-118): a later object wins an equal t.
-#define SHIM_BVH1_GROUP 4
-struct Bvh1Entry { uint32_t idx; float closest; int obj_face; uint32_t prim; };   // obj_face: obj | face << 16 | post << 24, obj = 0xffff: none
+// (measured 9 of 32 lanes active on the bunny config; 7 of 32 in the node loop with per-warp lists of 128 rays).
+// The closest hit of such a world is three launches:
+//   wf_bvh1_list    every ray against the list objects and the BVH's root boxes (full warps, streaming); the result
+//                   goes to a 16-byte record per ray, rays that can reach the tree are appended to a device-wide queue
+//   wf_bvh1_walk    persistent warps pull queue entries and walk them; a lane whose walk ends writes its result to
+//                   the ray's record and, once SHIM_BVH1_REFILL_IDLE lanes of the warp are idle, the idle lanes take
+//                   the next entries of the queue - no barrier anywhere, the warps stay dense until the queue of the
+//                   whole iteration is drained
+//   wf_bvh1_finish  every ray's record -> background / material queue (full warps, one atomic per group of lanes
+//                   with the same material kind)
+// List order is kept (hittable.rs:100-118): a later object wins an equal t.
+#ifndef SHIM_BVH1_REFILL_IDLE
+#define SHIM_BVH1_REFILL_IDLE 12
+#endif
+enum { BVH1_NONE = 0xffff, BVH1_DROP = 0xfffe };   // obj field of a record: no hit / path ends without a contribution
+// record: x = t bits, y = obj | face << 16 | post << 24 (post: the list hit comes after the Bvh in list order), z = prim_ref
 
-template <bool COUNT>
-__device__ __forceinline__ void bvh1_finish(const WfParams& p, const SceneView& sv, int cur, uint32_t i, bool valid, bool hit, const Hit& h) {
-    // miss -> background (ray.rs:60); hit -> append ray + hit record to the material queue (one atomic per group)
+// appends ray i + its hit record to the queue of the hit's material kind (all 32 lanes call; kind 7 = nothing to append)
+__device__ __forceinline__ void bvh1_append(const WfParams& p, int cur, uint32_t i, int kind, const f4& hv) {
     const uint32_t lane = threadIdx.x & 31u;
-    int kind = 7;
-    f4 hv;
-    if (valid) {
-        if (!hit) {
-            if (p.bg[0] != 0.0f || p.bg[1] != 0.0f || p.bg[2] != 0.0f) {
-                f4 t = p.thr[cur][i];
-                float* a = p.accum + 3 * (size_t)(uint32_t)f2i(t.w);
-                atomicAdd(a + 0, t.x * p.bg[0]);
-                atomicAdd(a + 1, t.y * p.bg[1]);
-                atomicAdd(a + 2, t.z * p.bg[2]);
-            }
-        } else {
-            const int mw = hit_material_word(sv, h);
-            const int mat = mat_word_index(mw);
-            kind = mat_word_kind(mw);
-            hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat);
-        }
-    }
-    unsigned grp = __match_any_sync(0xffffffffu, kind);
-    if (kind < MAT_KINDS) {
-        int leader = __ffs(grp) - 1;
+    const unsigned grp = __match_any_sync(0xffffffffu, kind);
+    if (kind < MAT_KINDS) {   // lanes with the same kind share one atomic
+        const int leader = __ffs(grp) - 1;
         uint32_t base = 0;
         if ((int)lane == leader) base = atomicAdd(p.cnt + CNT_MQ + kind, (uint32_t)__popc(grp));
         base = __shfl_sync(grp, base, leader);
-        size_t pos = mq_slot(p, 0, kind, base + (uint32_t)__popc(grp & ((1u << lane) - 1u)));
+        const size_t pos = mq_slot(p, 0, kind, base + (uint32_t)__popc(grp & ((1u << lane) - 1u)));
         p.mq_o[pos] = p.ray_o[cur][i]; p.mq_d[pos] = p.ray_d[cur][i]; p.mq_thr[pos] = p.thr[cur][i]; p.mq_hit[pos] = hv;
     }
 }
-
-template <bool COUNT, int ONLY = -1>
-__device__ __forceinline__ void extend_rays_bvh1(const WfParams& p, const SceneView& sv, int cur, uint32_t n, Bvh1Entry* entries_base) {
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5), warp_global = blockIdx.x * (blockDim.x >> 5) + warp;
-    Bvh1Entry* entries = entries_base + (size_t)warp * (SHIM_BVH1_GROUP * 32);
-    const int bo = p.bvh1_index;
-    const uint32_t group = SHIM_BVH1_GROUP * 32u;
-    TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
-    int stack[SHIM_BVH_STACK];
-    for (uint32_t base = warp_global * group; base < n; base += warps_total * group) {
-        uint32_t count = 0;
-        // ---- phase 1
-        for (uint32_t k = 0; k < SHIM_BVH1_GROUP; ++k) {
-            const uint32_t i = base + k * 32u + lane;
-            bool valid = i < n, need = false, hit = false;
-            Hit h; h.obj = -1; h.t = SHIM_INF; h.prim = 0; h.face = 0;
-            bool post = false;
-            if (valid) {
-                f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i];
-                Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
-                if (ray_has_nan(r)) {
-                    valid = false;   // see extend_rays: the path ends without a contribution
-                } else {
-                    float closest = SHIM_INF;
-                    for (int oi = 0; oi < sv.n_objects; ++oi) {
-                        if (oi == bo) continue;
-                        const DevObject& ob = sv.objects[oi];
-                        RayCtx pc;
-                        pc.r = object_ray(ob, r);
-                        float t; int face = 0;
-                        if (COUNT) tc.prims++;
-                        if (hit_prim(sv, (uint32_t)ob.ref, pc, 0.001f, closest, t, face)) {
-                            closest = t; h.t = t; h.obj = oi; h.prim = (uint32_t)ob.ref; h.face = face; post = oi > bo; hit = true;
-                        }
-                    }
-                    // can the ray reach the tree at all?  (the root's two child boxes, against the closest list hit)
-                    const DevObject& bob = sv.objects[bo];
-                    RayCtx c;
-                    make_ctx(c, object_ray(bob, r));
-                    const DevNode& rn = sv.nodes[bob.ref];
-                    f4 na = rn.a, nb = rn.b, nc = rn.c;
-                    float tl, tr;
-                    need = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, 0.001f, closest, tl) ||
-                           (rn.d.y != CHILD_NONE && slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, 0.001f, closest, tr));
-                }
-            }
-            const unsigned nmask = __ballot_sync(0xffffffffu, need);
-            if (need) {
-                Bvh1Entry e;
-                e.idx = i; e.closest = h.t; e.obj_face = (hit ? h.obj : 0xffff) | (h.face << 16) | ((post ? 1 : 0) << 24); e.prim = h.prim;
-                entries[count + (uint32_t)__popc(nmask & lt_mask)] = e;
-            }
-            count += (uint32_t)__popc(nmask);
-            bvh1_finish<COUNT>(p, sv, cur, i, valid && !need, hit, h);
+// a ray's final record -> background (ray.rs:60) or the material kind + hit record to append
+__device__ __forceinline__ int bvh1_resolve(const WfParams& p, const SceneView& sv, int cur, uint32_t i, const i4& rec, f4& hv) {
+    const int obj = rec.y & 0xffff;
+    if (obj == BVH1_DROP) return 7;
+    if (obj == BVH1_NONE) {
+        if (p.bg[0] != 0.0f || p.bg[1] != 0.0f || p.bg[2] != 0.0f) {
+            const f4 t = p.thr[cur][i];
+            float* a = p.accum + 3 * (size_t)(uint32_t)f2i(t.w);
+            atomicAdd(a + 0, t.x * p.bg[0]);
+            atomicAdd(a + 1, t.y * p.bg[1]);
+            atomicAdd(a + 2, t.z * p.bg[2]);
         }
-        __syncwarp();
-        // ---- phase 2: dense walks with refill.  Every lane owns one walk; all walks advance "to and through the next
-        // primitive test" together; once half of the lanes have finished (and entries are left), the finished lanes
-        // write their results and take the next entries of the warp's list.
-        uint32_t next = 0;
-        bool active = false, pending = false, hit = false;
-        uint32_t i = 0;
-        Hit h; h.obj = -1; h.t = SHIM_INF; h.prim = 0; h.face = 0;
-        bool post = false;
-        RayCtx c;
-        BvhWalk w;
-        bvh_walk_init(w, 0, 0.0f);
-        w.cur = SHIM_STACK_END;
-        const DevObject& bob = sv.objects[bo];
-        while (count > 0) {
-            if (__any_sync(0xffffffffu, pending)) {
-                if (pending && w.best.any && (!hit || w.best.t < h.t || !post)) {  // an equal t goes to the later list object
-                    h.t = w.best.t; h.obj = bo; h.prim = w.best.prim; h.face = w.best.face; hit = true;
-                }
-                bvh1_finish<COUNT>(p, sv, cur, i, pending, hit, h);
-                pending = false;
-            }
-            const unsigned idle = __ballot_sync(0xffffffffu, !active);
-            const uint32_t left = count - next;
-            if (left > 0 && idle) {
-                const uint32_t my = (uint32_t)__popc(idle & lt_mask);
-                if (!active && my < left) {
-                    const Bvh1Entry en = entries[next + my];
-                    i = en.idx;
-                    const int obj = en.obj_face & 0xffff;
-                    post = ((en.obj_face >> 24) & 1) != 0;
-                    hit = obj != 0xffff;
-                    h.t = en.closest; h.obj = hit ? obj : -1; h.prim = en.prim; h.face = (en.obj_face >> 16) & 0xff;
-                    f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i];
-                    Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
-                    make_ctx(c, object_ray(bob, r));
-                    bvh_walk_init(w, bob.ref, en.closest);
-                    active = true;
-                }
-                const uint32_t n_idle = (uint32_t)__popc(idle);
-                next += n_idle < left ? n_idle : left;
-            }
-            if (!__any_sync(0xffffffffu, active)) break;
-            for (;;) {
-                if (active) {
-                    bvh_walk_step<COUNT, ONLY>(sv, w, stack, c, 0.001f, &tc);
-                    if (bvh_walk_done(w)) { active = false; pending = true; }
-                }
-                const unsigned act = __ballot_sync(0xffffffffu, active);
-                if (act == 0u) break;
-                if (next < count && __popc(act) <= 16) break;
-            }
-        }
-        if (__any_sync(0xffffffffu, pending)) {
-            if (pending && w.best.any && (!hit || w.best.t < h.t || !post)) { h.t = w.best.t; h.obj = bo; h.prim = w.best.prim; h.face = w.best.face; hit = true; }
-            bvh1_finish<COUNT>(p, sv, cur, i, pending, hit, h);
-            pending = false;
-        }
-        __syncwarp();
+        return 7;
     }
-    if (COUNT) {
-        atomicAdd(cnt64(p.cnt, C64_NODES), (unsigned long long)tc.nodes);
-        atomicAdd(cnt64(p.cnt, C64_PRIMS), (unsigned long long)tc.prims);
-    }
+    Hit h; h.t = i2f(rec.x); h.obj = obj; h.prim = (uint32_t)rec.z; h.face = (rec.y >> 16) & 0xff;
+    const int mw = hit_material_word(sv, h);
+    hv.x = h.t; hv.y = i2f(h.obj | (h.face << 16)); hv.z = i2f((int)h.prim); hv.w = i2f(mat_word_index(mw));
+    return mat_word_kind(mw);
 }
 
-template <bool SMEM, bool COUNT, int THREADS = SHIM_EXTEND_THREADS, int ONLY = -1>
-__global__ void __launch_bounds__(THREADS, 1) wf_extend_bvh1() {
+template <bool COUNT>
+__global__ void __launch_bounds__(256) wf_bvh1_list() {
     const WfParams& p = g_p;
+    const SceneView& sv = p.sv;
     const int cur = (int)p.cnt[CNT_CUR];
     const uint32_t n = p.cnt[cur];
-    if (blockIdx.x * blockDim.x * SHIM_BVH1_GROUP >= n) return;
-    extern __shared__ __align__(128) unsigned char smem[];   // [scene image (SMEM)] [per-warp entry lists]
+    const uint32_t n_round = (n + 31u) & ~31u;
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    const int bo = p.bvh1_index;
+    uint32_t prims = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool need = false;
+        int kind = 7;
+        f4 hv;
+        if (i < n) {
+            f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i];
+            Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
+            i4 rec; rec.x = f2i(SHIM_INF); rec.y = BVH1_DROP; rec.z = 0; rec.w = 0;
+            if (!ray_has_nan(r)) {   // see extend_rays: a NaN ray ends its path without a contribution
+                float closest = SHIM_INF;
+                int obj = BVH1_NONE, face_hit = 0; uint32_t prim = 0; bool post = false;
+                for (int oi = 0; oi < sv.n_objects; ++oi) {
+                    if (oi == bo) continue;
+                    const DevObject& ob = sv.objects[oi];
+                    RayCtx pc;
+                    pc.r = object_ray(ob, r);
+                    float t; int face = 0;
+                    if (COUNT) prims++;
+                    if (hit_prim(sv, (uint32_t)ob.ref, pc, 0.001f, closest, t, face)) {
+                        closest = t; obj = oi; prim = (uint32_t)ob.ref; face_hit = face; post = oi > bo;
+                    }
+                }
+                // can the ray reach the tree at all?  (the root's two child boxes, against the closest list hit)
+                const DevObject& bob = sv.objects[bo];
+                RayCtx c;
+                make_ctx(c, object_ray(bob, r));
+                const DevNode& rn = sv.nodes[bob.ref];
+                f4 na = rn.a, nb = rn.b, nc = rn.c;
+                float tl, tr;
+                need = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, 0.001f, closest, tl) ||
+                       (rn.d.y != CHILD_NONE && slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, 0.001f, closest, tr));
+                rec.x = f2i(closest); rec.y = obj | (face_hit << 16) | ((post ? 1 : 0) << 24); rec.z = (int)prim;
+            }
+            if (need) p.bvh1_hit[i] = rec;                      // the walk may replace it, wf_bvh1_finish writes it out
+            else kind = bvh1_resolve(p, sv, cur, i, rec, hv);   // final already
+        }
+        const unsigned nmask = __ballot_sync(0xffffffffu, need);
+        if (nmask) {
+            uint32_t at = 0;
+            if (lane == (uint32_t)(__ffs(nmask) - 1)) at = atomicAdd(p.cnt + CNT_TREEQ, (uint32_t)__popc(nmask));
+            at = __shfl_sync(0xffffffffu, at, __ffs(nmask) - 1);
+            if (need) p.bvh1_queue[at + (uint32_t)__popc(nmask & lt_mask)] = i;
+        }
+        bvh1_append(p, cur, i, kind, hv);
+    }
+    if (COUNT) atomicAdd(cnt64(p.cnt, C64_PRIMS), (unsigned long long)prims);
+}
+
+#ifndef SHIM_BVH1_PRIM_BATCH
+#define SHIM_BVH1_PRIM_BATCH 8
+#endif
+template <bool SMEM, bool COUNT, int THREADS = SHIM_EXTEND_THREADS, int ONLY = -1>
+__global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
+    const WfParams& p = g_p;
+    const int cur_q = (int)p.cnt[CNT_CUR];
+    const uint32_t count = p.cnt[CNT_TREEQ];
+    if (blockIdx.x * blockDim.x >= count) return;   // fewer entries than one per thread up to this block: the others take them
+    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const SceneView sv = SMEM ? stage_scene(p, smem, &bar) : p.sv;
-    extend_rays_bvh1<COUNT, ONLY>(p, sv, cur, n, reinterpret_cast<Bvh1Entry*>(smem + (SMEM ? p.smem.total : 0u)));
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    const int bo = p.bvh1_index;
+    const DevObject& bob = sv.objects[bo];
+    uint32_t nodes = 0, prims = 0;
+    int stack[SHIM_BVH_STACK];
+    // Every lane owns one walk (the state of bvh_closest, resumable).  The warp alternates between rounds of node steps
+    // and rounds of primitive tests: a lane that has reached a primitive waits until SHIM_BVH1_PRIM_BATCH lanes have
+    // one (or no lane is left at an inner node), so that both kinds of rounds run with fuller warps than a loop in
+    // which every lane tests its primitive as soon as it gets there.
+    bool active = false, more = true;
+    uint32_t ray = 0;
+    float list_t = SHIM_INF;
+    bool list_hit = false, post = false;
+    RayCtx c;
+    BvhBest best; best.t = 0; best.prim = 0; best.face = 0; best.any = false;
+    float t_cull = 0;
+    int cur = SHIM_STACK_END, sp = 0;
+    while (more || __any_sync(0xffffffffu, active)) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (more && idle) {
+            const uint32_t n_idle = (uint32_t)__popc(idle);
+            uint32_t got = 0;
+            if (lane == (uint32_t)(__ffs(idle) - 1)) got = atomicAdd(p.cnt + CNT_TREEQ_NEXT, n_idle);
+            got = __shfl_sync(0xffffffffu, got, __ffs(idle) - 1);
+            const uint32_t my = got + (uint32_t)__popc(idle & lt_mask);
+            if (!active && my < count) {
+                ray = p.bvh1_queue[my];
+                const i4 rec = p.bvh1_hit[ray];
+                list_t = i2f(rec.x);
+                list_hit = (rec.y & 0xffff) != BVH1_NONE;
+                post = ((rec.y >> 24) & 1) != 0;
+                f4 o = p.ray_o[cur_q][ray], d = p.ray_d[cur_q][ray];
+                Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
+                make_ctx(c, object_ray(bob, r));
+                best.t = list_t; best.prim = 0; best.face = 0; best.any = false;
+                t_cull = list_t; sp = 0; cur = bob.ref;
+                active = true;
+            }
+            if (got + n_idle >= count) more = false;
+        }
+        if (!__any_sync(0xffffffffu, active)) continue;   // (`more` is false by now: the loop ends)
+        for (;;) {
+            // ---- node rounds
+            for (;;) {
+                const bool at_node = active && cur >= 0 && cur != SHIM_STACK_END;
+                const unsigned nm = __ballot_sync(0xffffffffu, at_node);
+                if (nm == 0u) break;
+                const unsigned pm = __ballot_sync(0xffffffffu, active && cur < 0);
+                if (__popc(pm) >= SHIM_BVH1_PRIM_BATCH) break;
+                if (at_node) {
+                    const DevNode& nd = sv.nodes[cur];
+                    f4 na = nd.a, nb = nd.b, nc = nd.c;
+                    i4 ch = nd.d;
+                    if (COUNT) nodes++;
+                    float tl, tr;
+                    bool hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, 0.001f, t_cull, tl);
+                    bool hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, 0.001f, t_cull, tr);
+                    hr = hr && ch.y != CHILD_NONE;
+                    if (hl && hr) {
+                        bool swap = tr < tl;
+                        cur = swap ? ch.y : ch.x;
+                        if (sp < SHIM_BVH_STACK) stack[sp++] = swap ? ch.x : ch.y;
+                    } else if (hl) {
+                        cur = ch.x;
+                    } else if (hr) {
+                        cur = ch.y;
+                    } else {
+                        cur = sp > 0 ? stack[--sp] : SHIM_STACK_END;
+                    }
+                }
+            }
+            // ---- one round of primitive tests (same rules as bvh_closest: closer wins, an exact tie goes to the later leaf)
+            if (active && cur < 0) {
+                const uint32_t ref = ~(uint32_t)cur;
+                float t; int face = 0;
+                if (COUNT) prims++;
+                if (hit_prim<ONLY>(sv, ref, c, 0.001f, t_cull, t, face) && !(t > best.t)) {
+                    bool take = !best.any || t < best.t;
+                    if (!take) take = tie_goes_to_candidate<ONLY>(sv, c, 0.001f, ref, best.prim, t);
+                    if (take) { best.t = t; best.prim = ref; best.face = face; best.any = true; t_cull = t + fabsf(t) * 3.8146973e-06f; }
+                }
+                cur = sp > 0 ? stack[--sp] : SHIM_STACK_END;
+            }
+            // ---- retire finished walks
+            if (active && cur == SHIM_STACK_END) {
+                active = false;
+                // an equal t goes to the later list object (hittable.rs:100-118)
+                if (best.any && (!list_hit || best.t < list_t || !post)) {
+                    i4 rec; rec.x = f2i(best.t); rec.y = bo | (best.face << 16); rec.z = (int)best.prim; rec.w = 0;
+                    p.bvh1_hit[ray] = rec;
+                }
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, active);
+            if (act == 0u) break;
+            if (more && __popc(act) <= 32 - SHIM_BVH1_REFILL_IDLE) break;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(cnt64(p.cnt, C64_NODES), (unsigned long long)nodes);
+        atomicAdd(cnt64(p.cnt, C64_PRIMS), (unsigned long long)prims);
+    }
 }
-#define SHIM_BVH1_SMEM_BYTES_T(T) (((T) / 32) * SHIM_BVH1_GROUP * 32 * (int)sizeof(Bvh1Entry))
-#define SHIM_BVH1_SMEM_BYTES SHIM_BVH1_SMEM_BYTES_T(1024)   /* reserved for the largest block variant */
+
+// the rays that went through the tree walk: record -> background / material queue (full warps)
+__global__ void __launch_bounds__(256) wf_bvh1_finish() {
+    const WfParams& p = g_p;
+    const SceneView& sv = p.sv;
+    const int cur = (int)p.cnt[CNT_CUR];
+    const uint32_t n = p.cnt[CNT_TREEQ];
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+        int kind = 7;
+        f4 hv;
+        uint32_t i = 0;
+        if (j < n) {
+            i = p.bvh1_queue[j];
+            kind = bvh1_resolve(p, sv, cur, i, p.bvh1_hit[i], hv);
+        }
+        bvh1_append(p, cur, i, kind, hv);
+    }
+}
 
 // ---------------------------------------------------------------------------- shade
 struct ShadeOut { bool cont; Ray ray; f3 thr; };
