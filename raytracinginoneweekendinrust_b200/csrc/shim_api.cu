@@ -394,6 +394,13 @@ static void choose_variant(const shim_scene* s, const shim::DeviceState* st, con
         *use_smem_out = true;
     }
     k.bvh1_tri_threads = 0;
+    k.bvh1_list_rects = 0;
+    if (k.bvh1_index >= 0 && f.objects.size() - 1 <= SHIM_BVH1_LIST_RECTS) {
+        bool plain_rects = true;
+        for (size_t i = 0; i < f.objects.size(); ++i)
+            if ((int)i != k.bvh1_index && (f.objects[i].kind != OBJ_PRIM || f.objects[i].flags != 0 || prim_type((uint32_t)f.objects[i].ref) != PT_RECT)) plain_rects = false;
+        k.bvh1_list_rects = plain_rects ? 1 : 0;
+    }
     if (k.bvh1_index >= 0 && f.sph_s.empty() && f.msph.empty() && f.cube.empty() && !f.tri.empty() && !sw.no_bvh1_tri) {
         // plain objects are rects, so every primitive inside the Bvh is a triangle ...
         bool rects_outside = true;
@@ -446,7 +453,9 @@ static void launch_extend(const Wavefront& w, const WfParams& k, bool use_smem, 
     const uint32_t smem = use_smem ? k.smem.total : 0;
     const bool S = use_smem, C = k.count_nodes != 0, M = k.has_media != 0, H = k.use_hrpp != 0;
     if (k.bvh1_index >= 0) {  // one BVH among plain objects, no medium, no predictor: list pass, dense tree walk, finish pass
-        if (C) wf_bvh1_list<true><<<w.grid_stream, 256, 0, st>>>(); else wf_bvh1_list<false><<<w.grid_stream, 256, 0, st>>>();
+        if (C) wf_bvh1_list<true><<<w.grid_stream, 256, 0, st>>>();
+        else if (k.bvh1_list_rects) wf_bvh1_list<false, true><<<w.grid_stream, 256, 0, st>>>();
+        else wf_bvh1_list<false><<<w.grid_stream, 256, 0, st>>>();
         const int wgrid = S ? w.sm_count : w.grid_bvh1_walk;
         if (k.bvh1_tri_threads && !C) {   // triangle-only tree: no primitive dispatch, more warps
             if (S) wf_bvh1_walk<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<wgrid, SHIM_BVH1_TRI_THREADS, smem, st>>>();
@@ -530,7 +539,7 @@ static bool under_profiler() {
 static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
     // everything launch_iteration branches on (the launches themselves take no arguments)
     const Wavefront::GraphKey key(use_smem ? k.smem.total : 0u, use_smem ? 1 : 0, k.count_nodes != 0, k.has_media != 0, k.use_hrpp != 0,
-                                  k.bvh1_index >= 0, k.bvh1_tri_threads, k.list_threads, k.solo, k.solo_only, k.fused_generate, k.trace_pipeline);
+                                  k.bvh1_index >= 0 ? 1 + k.bvh1_list_rects : 0, k.bvh1_tri_threads, k.list_threads, k.solo, k.solo_only, k.fused_generate, k.trace_pipeline);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));

@@ -73,6 +73,7 @@ struct WfParams {
     float bg[3];
     uint64_t seed;
     int has_media, count_nodes, use_hrpp;
+    int bvh1_list_rects;    // the plain objects next to the one Bvh are untransformed rects, at most SHIM_BVH1_LIST_RECTS of them
     int bvh1_tri_threads;   // > 0: the one Bvh holds only triangles: wf_bvh1_walk<.., THREADS, PT_TRI>
     int list_threads; // > 0: the world has no Bvh: wf_extend_list with this many threads per block
     int trace_pipeline;   // the iteration is wf_trace (shade -> closest hit) + wf_tail_mq (endgame, loop condition, next counters); no ray queues
@@ -423,7 +424,11 @@ __device__ __forceinline__ int bvh1_resolve(const WfParams& p, const SceneView& 
     return mat_word_kind(mw);
 }
 
-template <bool COUNT>
+// RECTS: every list object is a plain rect (the Cornell walls of the mesh scenes) and there are at most
+// SHIM_BVH1_LIST_RECTS of them: their records are copied to shared memory once per block and tested without the
+// per-object transform and primitive dispatch (818 -> ~400 thread instructions per ray on the bunny config)
+#define SHIM_BVH1_LIST_RECTS 16
+template <bool COUNT, bool RECTS = false>
 __global__ void __launch_bounds__(256) wf_bvh1_list() {
     const WfParams& p = g_p;
     const SceneView& sv = p.sv;
@@ -433,6 +438,18 @@ __global__ void __launch_bounds__(256) wf_bvh1_list() {
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const int bo = p.bvh1_index;
     uint32_t prims = 0;
+    __shared__ f4 s_rect[2 * SHIM_BVH1_LIST_RECTS];
+    __shared__ int s_obj[SHIM_BVH1_LIST_RECTS], s_ref[SHIM_BVH1_LIST_RECTS];
+    if (RECTS) {
+        if ((int)threadIdx.x < sv.n_objects && (int)threadIdx.x != bo) {
+            const int m = (int)threadIdx.x - ((int)threadIdx.x > bo ? 1 : 0);   // list order is kept
+            const int ref = sv.objects[threadIdx.x].ref;
+            s_obj[m] = (int)threadIdx.x; s_ref[m] = ref;
+            s_rect[2 * m] = sv.rect[2 * (size_t)prim_index((uint32_t)ref)];
+            s_rect[2 * m + 1] = sv.rect[2 * (size_t)prim_index((uint32_t)ref) + 1];
+        }
+        __syncthreads();
+    }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool need = false;
         int kind = 7;
@@ -444,15 +461,22 @@ __global__ void __launch_bounds__(256) wf_bvh1_list() {
             if (!ray_has_nan(r)) {   // see extend_rays: a NaN ray ends its path without a contribution
                 float closest = SHIM_INF;
                 int obj = BVH1_NONE, face_hit = 0; uint32_t prim = 0; bool post = false;
-                for (int oi = 0; oi < sv.n_objects; ++oi) {
-                    if (oi == bo) continue;
-                    const DevObject& ob = sv.objects[oi];
-                    RayCtx pc;
-                    pc.r = object_ray(ob, r);
-                    float t; int face = 0;
-                    if (COUNT) prims++;
-                    if (hit_prim(sv, (uint32_t)ob.ref, pc, 0.001f, closest, t, face)) {
-                        closest = t; obj = oi; prim = (uint32_t)ob.ref; face_hit = face; post = oi > bo;
+                if (RECTS) {
+                    for (int m = 0; m < sv.n_objects - 1; ++m) {
+                        float t;
+                        if (hit_rect(s_rect + 2 * m, r, 0.001f, closest, t)) { closest = t; obj = s_obj[m]; prim = (uint32_t)s_ref[m]; post = obj > bo; }
+                    }
+                } else {
+                    for (int oi = 0; oi < sv.n_objects; ++oi) {
+                        if (oi == bo) continue;
+                        const DevObject& ob = sv.objects[oi];
+                        RayCtx pc;
+                        pc.r = object_ray(ob, r);
+                        float t; int face = 0;
+                        if (COUNT) prims++;
+                        if (hit_prim(sv, (uint32_t)ob.ref, pc, 0.001f, closest, t, face)) {
+                            closest = t; obj = oi; prim = (uint32_t)ob.ref; face_hit = face; post = oi > bo;
+                        }
                     }
                 }
                 // can the ray reach the tree at all?  (the root's two child boxes, against the closest list hit)
