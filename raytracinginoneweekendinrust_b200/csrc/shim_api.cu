@@ -506,7 +506,8 @@ static void launch_trace(const Wavefront& w, const WfParams& k, cudaStream_t st)
     else wf_trace_solo<SHIM_SOLO_ANY_THREADS, -1><<<w.sm_count, SHIM_SOLO_ANY_THREADS, k.smem.total, st>>>();
 }
 static void launch_tail_mq(const Wavefront& w, const WfParams& k, cudaStream_t st) {
-    if (k.solo_only == PT_SPHERE) wf_tail_mq<PT_SPHERE><<<w.grid_tail, 128, 0, st>>>(); else wf_tail_mq<-1><<<w.grid_tail, 128, 0, st>>>();
+    const int grid = w.sm_count * SHIM_TAIL_MQ_BLOCKS;
+    if (k.solo_only == PT_SPHERE) wf_tail_mq<PT_SPHERE><<<grid, 128, 0, st>>>(); else wf_tail_mq<-1><<<grid, 128, 0, st>>>();
 }
 // one wavefront iteration on `st` (the parameters are already in constant memory, the queue index in the counters)
 static void launch_iteration(const Wavefront& w, const WfParams& k, bool use_smem, cudaStream_t st) {

@@ -909,8 +909,11 @@ __global__ void __launch_bounds__(THREADS, 1) wf_trace_solo() {
 }
 
 // wf_tail for the trace pipeline: the survivors are material-queue entries (hits waiting to be shaded)
+#ifndef SHIM_TAIL_MQ_BLOCKS
+#define SHIM_TAIL_MQ_BLOCKS 4   // blocks of 128 threads per SM (one path per thread)
+#endif
 template <int ONLY>
-__global__ void __launch_bounds__(128) wf_tail_mq() {
+__global__ void __launch_bounds__(128, SHIM_TAIL_MQ_BLOCKS) wf_tail_mq() {
     const WfParams& p = g_p;
     // Thread 0 reads the counters once and the block branches on that copy: the last block to take a ticket rewrites
     // them (next iteration), so no thread may look at global memory again after its block's ticket is taken.
