@@ -343,13 +343,17 @@ def measure_extra(label, key, kw, with_cpu, args, api, capi, scenes, torch, dev,
            "ms_per_step": ms / len(ev), "steps": len(ev), "rays_per_sample": rays / max(1, sum(s.samples for s in stats)),
            "iterations_per_step": stats[-1].iterations, "gpu_launches_per_step": int(stats[-1].kernel_launches),
            "scene_device_bytes": scene.device_bytes(), "pool_bytes": int(stats[-1].pool_bytes), "host_scene_build_s": build_s}
-    kernel = capi.Stats.EXTEND_KERNELS.get(int(stats[-1].extend_variant), "wf_extend")
+    kernel = capi.Stats.EXTEND_KERNELS.get(int(stats[-1].extend_variant), "wf_extend")   # (wf_bvh1_walk: timed with wf_bvh1_list and wf_bvh1_finish)
     if info.predictors:
         st = stats[-1]
         tot = st.hrpp_true_positive + st.hrpp_false_positive + st.hrpp_no_prediction
         out["hrpp"] = {"true_positive": st.hrpp_true_positive / max(1, tot), "false_positive": st.hrpp_false_positive / max(1, tot),
                        "no_prediction": st.hrpp_no_prediction / max(1, tot), "lookups": int(tot),
-                       "note": "predictions return the first hit found in a predicted leaf (bvh.rs:145-156): the image is approximate by design"}
+                       "note": "predictions return the first hit found in a predicted leaf (bvh.rs:145-156): the image is approximate by design",
+                       "verdict": "measured for parity with Bvh::with_predictor, not a speed feature: predictions land only for camera rays of "
+                                  "later samples of a pixel (diffuse bounce rays never repeat a 48-bit key), and a table probe plus the "
+                                  "false-positive re-walks cost more than the ~10 node visits of a SAH walk - compare `value` with the "
+                                  "predictor-off entry of the same config (DESIGN.md 5b)"}
         kernel = "wf_extend<HRPP>"
     # roofline: node / primitive counters from a 1-spp counting render (predictor off: the counters need the plain walk)
     if not info.predictors:

@@ -64,6 +64,9 @@ def main(argv=None) -> int:
               f"Ratio true positive:        {st.hrpp_true_positive / max(1, total)}\nFalse positive predictions: {st.hrpp_false_positive}\n"
               f"Ratio false positive:       {st.hrpp_false_positive / max(1, total)}\nNo predictions:             {st.hrpp_no_prediction}\n"
               f"Ratio no predictions:       {st.hrpp_no_prediction / max(1, total)}", file=sys.stderr)
+    for bvh in info.bvhs:                                         # bvh.rs:221-227: every Bvh reports itself when it is dropped
+        n_nodes, root, height = world.bvh_info(bvh)
+        print(f"BVH id: {bvh}\nBVH height: {height}\n\n", file=sys.stderr)   # (the reference's id is a random uuid; here the hittable id)
     print(f"Render time: {time.perf_counter() - start:.6f}s  ({st.rays} rays, {st.samples} samples, device {st.device_ms:.3f} ms, "
           f"{st.rays / st.device_ms / 1e3:.1f} Mrays/s)", file=sys.stderr)
     return 0

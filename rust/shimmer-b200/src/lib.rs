@@ -172,6 +172,18 @@ impl Scene {
         check(unsafe { sys::shim_render(self.raw, cam, p, out.as_mut_ptr(), &mut st) })?;
         Ok(st)
     }
+    /// One image over several devices of this process (`shim_render_multi`): `devices` = CUDA ordinals (empty = all),
+    /// `tiles` = shard by tile index instead of by sample range.  The combined mean lands in `out`.
+    pub fn render_multi(&mut self, cam: &Camera, p: &RenderParams, devices: &[i32], tiles: bool, out: &mut [f32]) -> Result<Stats> {
+        if out.len() != p.width as usize * p.height as usize * 3 {
+            return Err(Error { code: sys::SHIM_ERR_INVALID, message: "render_multi: framebuffer size".into() });
+        }
+        let mut st = Stats::default();
+        let mode = if tiles { sys::SHIM_SHARD_TILES } else { sys::SHIM_SHARD_SAMPLES };
+        let ptr = if devices.is_empty() { std::ptr::null() } else { devices.as_ptr() };
+        check(unsafe { sys::shim_render_multi(self.raw, cam, p, devices.len() as c_int, ptr, mode, out.as_mut_ptr(), &mut st) })?;
+        Ok(st)
+    }
     /// Gate-1 query: closest hit of `rays` (7 floats each: origin, direction, time) -> (primitive id or -1, t).
     pub fn trace_closest(&mut self, rays: &[f32], t_min: f32, t_max: f32, seed: u64) -> Result<(Vec<i32>, Vec<f32>)> {
         if rays.len() % 7 != 0 {
@@ -215,6 +227,11 @@ impl Drop for HostFramebuffer {
     fn drop(&mut self) {
         unsafe { sys::shim_host_free(self.ptr) }
     }
+}
+
+/// Releases every device's wavefront pool (`shim_shutdown`); scenes stay valid.  No render may be in flight.
+pub fn shutdown() {
+    unsafe { sys::shim_shutdown() };
 }
 
 /// `Renderer::write_ppm` (renderer.rs:107-127): P3 text, no gamma, top row first; `None` = stdout.
