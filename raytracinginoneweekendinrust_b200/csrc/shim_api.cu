@@ -166,7 +166,7 @@ struct shim::DeviceState {
     SmemLayout smem_signed;            // ... with SNodes, for the one-Bvh kernels (total 0: not built)
     int n_predictors = 0, hrpp_log2 = 21;
     int primary = -1;                  // the device shim_commit uploaded to
-    uint32_t kinds_mask = 0;           // material kinds the scene holds (bit k = MatKind k)
+    uint32_t kinds_mask = 0;           // shading classes the scene holds (bit k = MatKind k, bit 5 = MQ_SLOW_LAMBERTIAN)
     std::mutex m;                      // guards `on`
     std::map<int, std::unique_ptr<DeviceScene>> on;
     ~DeviceState() { for (auto& kv : on) kv.second->release(); }
@@ -294,10 +294,11 @@ SHIM_API int shim_commit(shim_scene* s) {
     lap("blob");
     st->n_predictors = (int)f.predictor_bvh.size();
     if (const char* e = getenv("SHIM_HRPP_LOG2")) { int x = atoi(e); if (x >= 8 && x <= 26) st->hrpp_log2 = x; }
-    for (size_t i = 0; i + 1 < f.materials.size(); i += 2) {
+    for (size_t i = 0; i + 1 < f.materials.size(); i += 2) {   // shading classes the scene can queue hits for
         const int kind = f2i(f.materials[i].x);
         if (kind >= 0 && kind < MAT_KINDS) st->kinds_mask |= 1u << kind;
     }
+    if (f.slow_lambertians) st->kinds_mask |= 1u << MQ_SLOW_LAMBERTIAN;
     st->primary = device;
     DeviceScene* ds = nullptr;
     rc = upload_scene(st.get(), device, &ds);
@@ -426,7 +427,7 @@ static int wf_reserve(Wavefront& w, const shim::DeviceState* st, const shim_rend
     k.pool = pool;
     // material queues: only the kinds the scene has, two kinds per pool-sized region (one up, one down)
     int n_kinds = 0;
-    for (int kind = 0; kind < MAT_KINDS; ++kind) {
+    for (int kind = 0; kind < MQ_CLASSES; ++kind) {
         k.mq_first[kind] = 0; k.mq_dir[kind] = 1;
         if (!(st->kinds_mask & (1u << kind))) continue;
         const long long region = n_kinds / 2;

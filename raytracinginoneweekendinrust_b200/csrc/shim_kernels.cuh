@@ -32,12 +32,14 @@
 
 namespace shim {
 
-enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..6 */, CNT_CUR = 7, CNT_TICKET = 8, CNT_NEXT_CUR = 9, CNT_DONE = 10, CNT_ITER = 11,
-       CNT_BODIES = 12 /* iteration bodies executed */, CNT_GEN_BASE = 13 /* fused generation: queue slot of the first new sample */, CNT_U64_BASE = 14 /* u64 slots from here, as pairs */,
-       CNT_TREEQ = 30 /* one-Bvh worlds: rays queued for the tree walk */, CNT_TREEQ_NEXT = 31 /* ... handed out */,
-       CNT_MQ1 = 32 /* ..36: second material-queue counter set (wf_trace pipeline) */, CNT_GEN_N = 37 /* new samples of this iteration */ };
+enum { CNT_NRAYS0 = 0, CNT_NRAYS1 = 1, CNT_MQ = 2 /* ..7: one per shading class */, CNT_CUR = 8, CNT_TICKET = 9, CNT_NEXT_CUR = 10, CNT_DONE = 11, CNT_ITER = 12,
+       CNT_BODIES = 13 /* iteration bodies executed */, CNT_GEN_BASE = 14 /* fused generation: queue slot of the first new sample */,
+       CNT_GEN_N = 15 /* new samples of this iteration */, CNT_U64_BASE = 16 /* u64 slots from here, as pairs: ..31 */,
+       CNT_TREEQ = 32 /* one-Bvh worlds: rays queued for the tree walk */, CNT_TREEQ_NEXT = 33 /* ... handed out */,
+       CNT_MQ1 = 34 /* ..39: second material-queue counter set (wf_trace pipeline) */ };
 enum { C64_NEXT_SAMPLE = 0, C64_RAYS = 1, C64_NODES = 2, C64_PRIMS = 3, C64_HRPP_TP = 4, C64_HRPP_FP = 5, C64_HRPP_NONE = 6, C64_GEN_FIRST = 7, C64_COUNT = 8 };
 enum { CNT_WORDS = 40 };
+static_assert(CNT_MQ + MQ_CLASSES <= CNT_CUR && CNT_U64_BASE + 2 * C64_COUNT <= CNT_TREEQ && CNT_MQ1 + MQ_CLASSES <= CNT_WORDS, "counter layout");
 
 // shared-memory image of the scene arrays wf_extend walks (byte offsets, all multiples of 16)
 struct SmemLayout {
@@ -59,8 +61,8 @@ struct WfParams {
     // at most `pool`), and only the kinds the scene has get a region: entry j of kind k is mq_first[k] + mq_dir[k] * j
     f4* mq_o; f4* mq_d; f4* mq_thr;
     f4* mq_hit;     // t, obj | face << 16, prim_ref, material
-    long long mq_first[MAT_KINDS];
-    int mq_dir[MAT_KINDS];
+    long long mq_first[MQ_CLASSES];
+    int mq_dir[MQ_CLASSES];
     long long mq_set_stride;
     uint32_t* cnt;
     float* accum;   // W*H*3 radiance sums
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(256) wf_generate() {
             c[cur] = n_cur + n;
             c[1 - cur] = 0;
 #pragma unroll
-            for (int k = 0; k < MAT_KINDS; ++k) c[CNT_MQ + k] = 0;
+            for (int k = 0; k < MQ_CLASSES; ++k) c[CNT_MQ + k] = 0;
             c[CNT_TREEQ] = 0; c[CNT_TREEQ_NEXT] = 0;
             *cnt64(c, C64_RAYS) += (unsigned long long)(n_cur + n);
             c[CNT_ITER] += (n_cur + n == 0) ? 0u : 1u;
@@ -259,7 +261,7 @@ __device__ __forceinline__ void extend_rays(const WfParams& p, const SceneView& 
         }
         // append to the material queue: lanes that hit the same kind share one atomic
         unsigned grp = __match_any_sync(0xffffffffu, kind);
-        if (kind < MAT_KINDS) {
+        if (kind < MQ_CLASSES) {
             int leader = __ffs(grp) - 1;
             uint32_t base = 0;
             if ((int)lane == leader) base = atomicAdd(p.cnt + CNT_MQ + kind, (uint32_t)__popc(grp));
@@ -395,7 +397,7 @@ enum { BVH1_NONE = 0xffff, BVH1_DROP = 0xfffe };   // obj field of a record: no 
 __device__ __forceinline__ void bvh1_append(const WfParams& p, int cur, uint32_t i, int kind, const f4& hv) {
     const uint32_t lane = threadIdx.x & 31u;
     const unsigned grp = __match_any_sync(0xffffffffu, kind);
-    if (kind < MAT_KINDS) {   // lanes with the same kind share one atomic
+    if (kind < MQ_CLASSES) {   // lanes with the same kind share one atomic
         const int leader = __ffs(grp) - 1;
         uint32_t base = 0;
         if ((int)lane == leader) base = atomicAdd(p.cnt + CNT_MQ + kind, (uint32_t)__popc(grp));
@@ -667,14 +669,14 @@ __device__ __forceinline__ void shade_one(const WfParams& p, const SceneView& sv
     }
 }
 
-template <int KIND>
+template <int KIND, int QUEUE = KIND>
 __device__ __forceinline__ void shade_chunk(const WfParams& p, int cur, uint32_t j, uint32_t n) {
     const int nxt = 1 - cur;
     ShadeOut so;
     so.cont = false; so.ray.o = mk3(0, 0, 0); so.ray.d = mk3(0, 0, 0); so.ray.time = 0; so.thr = mk3(0, 0, 0);
     uint32_t bs = 0, pixel = 0;
     if (j < n) {
-        size_t q = mq_slot(p, 0, KIND, j);
+        size_t q = mq_slot(p, 0, QUEUE, j);
         f4 o = p.mq_o[q], d = p.mq_d[q], t = p.mq_thr[q], hv = p.mq_hit[q];
         Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
         bs = (uint32_t)f2i(d.w); pixel = (uint32_t)f2i(t.w);
@@ -699,19 +701,20 @@ __device__ __forceinline__ void shade_chunk(const WfParams& p, int cur, uint32_t
 __global__ void __launch_bounds__(256) wf_shade() {
     const WfParams& p = g_p;
     const int cur = (int)p.cnt[CNT_CUR];
-    uint32_t n[MAT_KINDS], first[MAT_KINDS + 1];
+    uint32_t n[MQ_CLASSES], first[MQ_CLASSES + 1];
     first[0] = 0;
 #pragma unroll
-    for (int k = 0; k < MAT_KINDS; ++k) {
+    for (int k = 0; k < MQ_CLASSES; ++k) {
         n[k] = p.cnt[CNT_MQ + k];
         first[k + 1] = first[k] + (n[k] + 255u) / 256u;
     }
-    for (uint32_t w = blockIdx.x; w < first[MAT_KINDS]; w += gridDim.x) {
+    for (uint32_t w = blockIdx.x; w < first[MQ_CLASSES]; w += gridDim.x) {
         if (w < first[1]) shade_chunk<MAT_LAMBERTIAN>(p, cur, (w - first[0]) * 256u + threadIdx.x, n[0]);
         else if (w < first[2]) shade_chunk<MAT_METAL>(p, cur, (w - first[1]) * 256u + threadIdx.x, n[1]);
         else if (w < first[3]) shade_chunk<MAT_DIELECTRIC>(p, cur, (w - first[2]) * 256u + threadIdx.x, n[2]);
         else if (w < first[4]) shade_chunk<MAT_DIFFUSE_LIGHT>(p, cur, (w - first[3]) * 256u + threadIdx.x, n[3]);
-        else shade_chunk<MAT_ISOTROPIC>(p, cur, (w - first[4]) * 256u + threadIdx.x, n[4]);
+        else if (w < first[5]) shade_chunk<MAT_ISOTROPIC>(p, cur, (w - first[4]) * 256u + threadIdx.x, n[4]);
+        else shade_chunk<MAT_LAMBERTIAN, MQ_SLOW_LAMBERTIAN>(p, cur, (w - first[5]) * 256u + threadIdx.x, n[5]);   // expensive textures, dense
     }
 }
 
@@ -790,6 +793,7 @@ __global__ void __launch_bounds__(128) wf_tail() {
             ShadeOut so;
             so.cont = false;
             switch (mat_word_kind(mw)) {
+            case MQ_SLOW_LAMBERTIAN:
             case MAT_LAMBERTIAN: shade_one<MAT_LAMBERTIAN>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
             case MAT_METAL: shade_one<MAT_METAL>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;
             case MAT_DIELECTRIC: shade_one<MAT_DIELECTRIC>(p, p.sv, r, h, mat, thr, bounce, pixel, sample, so); break;

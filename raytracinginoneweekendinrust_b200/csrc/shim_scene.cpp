@@ -342,9 +342,20 @@ struct Flattener {
 
     int fail(int code, const std::string& m) { sb.err = m; status = code; return code; }
     // material reference as the device stores it: index | kind << 28 (shim_device.h: mat_word_index / mat_word_kind)
-    int material_word(int mi) const {
+    // The kind field is the shading class (shim_types.h): a Lambertian whose texture tree holds a marble goes to the
+    // class of its own - except in worlds that are one plain Bvh, whose pipeline keeps the five kinds.
+    bool texture_is_slow(int t, int depth = 0) const {
+        if (t < 0 || (size_t)t >= sb.textures.size() || depth > 8) return false;
+        const HostTexture& x = sb.textures[t];
+        if (x.kind == TEX_MARBLE) return true;
+        return x.kind == TEX_CHECKER && (texture_is_slow(x.even, depth + 1) || texture_is_slow(x.odd, depth + 1));
+    }
+    int material_word(int mi) {
         if (mi < 0 || (size_t)mi >= sb.materials.size()) return mi;
-        return (int)((uint32_t)mi | ((uint32_t)sb.materials[mi].kind << 28));
+        int cls = sb.materials[mi].kind;
+        const bool one_plain_bvh = sb.world.size() == 1 && sb.ok_hit(sb.world[0]) && sb.hittables[sb.world[0]].kind == H_BVH;
+        if (cls == MAT_LAMBERTIAN && !one_plain_bvh && texture_is_slow(sb.materials[mi].tex)) { cls = MQ_SLOW_LAMBERTIAN; fs.slow_lambertians = true; }
+        return (int)((uint32_t)mi | ((uint32_t)cls << 28));
     }
 
     uint32_t add_prim(int hid) {

@@ -58,6 +58,7 @@ struct FlatScene {
     std::vector<uint8_t> images, perlin;
     std::vector<int> handle[5], rank[5], leaf[5], sibling[5];
     std::vector<int> predictor_bvh;  // hittable id of each BVH that carries a predictor
+    bool slow_lambertians = false;   // some material references carry the class MQ_SLOW_LAMBERTIAN (shim_types.h)
     SceneView view() const;          // pointers into the host vectors
     uint64_t bytes() const;
 };

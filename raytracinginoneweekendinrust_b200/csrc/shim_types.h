@@ -43,6 +43,12 @@ SHIM_HD float i2f(int i) {
 
 enum PrimType { PT_SPHERE = 0, PT_MSPHERE = 1, PT_RECT = 2, PT_TRI = 3, PT_CUBE = 4, PT_NONE = 7 };
 enum MatKind { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4, MAT_KINDS = 5 };
+// Material queues are per shading CLASS: the five kinds plus one for Lambertians whose texture is expensive (marble:
+// four f64 Perlin fBm evaluations, thousands of instructions).  In a queue shared with solid colours a warp ran that
+// code for one or two lanes while the others waited (showcase: wf_shade at 9.7 of 32 lanes); in a queue of their
+// own those hits fill whole warps.  The class travels in the kind field of a stored material reference; the trace
+// pipeline (one-Bvh worlds) keeps the five kinds.
+enum { MQ_SLOW_LAMBERTIAN = 5, MQ_CLASSES = 6 };
 enum TexKind { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_MARBLE = 2, TEX_IMAGE = 3 };
 enum { STAGE_CAMERA = 0, STAGE_INTERSECT = 1, STAGE_SCATTER = 2 };
 // mirror shim_status in include/shimmer_b200.h
