@@ -331,6 +331,7 @@ static int wf_init(Wavefront& w, int device) {
     CU(opt_in_smem(wf_bvh1_walk<true, false>, dyn));  CU(opt_in_smem(wf_bvh1_walk<true, true>, dyn));
     CU(opt_in_smem(wf_bvh1_walk<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI>, dyn));
     CU(opt_in_smem(wf_extend_list<false, SHIM_LIST_THREADS>, dyn)); CU(opt_in_smem(wf_extend_list<true, SHIM_LIST_THREADS>, dyn));
+    CU(opt_in_smem(wf_extend_list<false, SHIM_LIST_THREADS, true>, dyn)); CU(opt_in_smem(wf_extend_list<true, SHIM_LIST_THREADS, true>, dyn));
     CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, false>, dyn));
     CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, true>, dyn));
     CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_ANY_THREADS, -1, false>, dyn));
@@ -413,7 +414,10 @@ static void choose_variant(const shim_scene* s, const shim::DeviceState* st, con
         if (rects_outside && top_rects * 2 == f.rect.size()) k.bvh1_tri_threads = SHIM_BVH1_TRI_THREADS;
     }
     k.list_threads = 0;
-    if (use_smem && !k.count_nodes && !k.use_hrpp && f.nodes.empty() && !k.solo && !sw.no_list) k.list_threads = SHIM_LIST_THREADS;
+    if (use_smem && !k.count_nodes && !k.use_hrpp && f.nodes.empty() && !k.solo && !sw.no_list) {
+        k.list_threads = SHIM_LIST_THREADS;
+        k.fused_generate = sw.no_fuse ? 0 : 1;   // camera rays of new samples are made inside wf_extend_list
+    }
     k.tail_threshold = sw.tail >= 0 ? (uint32_t)sw.tail : 65536u;   // measured on Book-1: 32 k 3.40 ms, 48 k 3.38, 64 k 3.35, 96 k 3.48
 }
 
@@ -470,7 +474,10 @@ static void launch_extend(const Wavefront& w, const WfParams& k, bool use_smem, 
         return;
     }
     if (k.list_threads) {   // no Bvh in the world, scene image in shared memory
-        if (M) wf_extend_list<true, SHIM_LIST_THREADS><<<grid, SHIM_LIST_THREADS, smem, st>>>();
+        if (k.fused_generate) {
+            if (M) wf_extend_list<true, SHIM_LIST_THREADS, true><<<grid, SHIM_LIST_THREADS, smem, st>>>();
+            else wf_extend_list<false, SHIM_LIST_THREADS, true><<<grid, SHIM_LIST_THREADS, smem, st>>>();
+        } else if (M) wf_extend_list<true, SHIM_LIST_THREADS><<<grid, SHIM_LIST_THREADS, smem, st>>>();
         else wf_extend_list<false, SHIM_LIST_THREADS><<<grid, SHIM_LIST_THREADS, smem, st>>>();
         return;
     }

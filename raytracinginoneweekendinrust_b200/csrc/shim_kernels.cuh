@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_solo() {
 
 // wf_extend for worlds without any Bvh (flat lists like the Cornell scenes, main.rs:477-557): the tree walk and its
 // stack are compiled out, which frees registers for more resident warps.
-template <bool MEDIA, int THREADS>
+template <bool MEDIA, int THREADS, bool FUSE = false>
 __global__ void __launch_bounds__(THREADS, 1) wf_extend_list() {
     const WfParams& p = g_p;
     const int cur = (int)p.cnt[CNT_CUR];
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_list() {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     SceneView sv = stage_scene(p, smem, &bar);
-    extend_rays<false, MEDIA, false, false, -1, false>(p, sv, cur, n);
+    extend_rays<false, MEDIA, false, false, -1, false, FUSE>(p, sv, cur, n);
 }
 
 // ---------------------------------------------------------------------------- extend, one-BVH worlds
