@@ -72,10 +72,10 @@ struct DeviceGuard {
 // device.  It is kept after commit so that shim_render_multi can replicate the scene on further devices.
 struct SceneBlob {
     std::vector<unsigned char> bytes;
-    size_t o_nodes = 0, o_snodes = 0, o_sph = 0, o_sph_s = 0, o_sph_mat = 0, o_msph = 0, o_rect = 0, o_tri = 0, o_cube = 0, o_obj = 0, o_mat = 0, o_tex = 0,
+    size_t o_nodes = 0, o_snodes = 0, o_qnodes = 0, o_sph = 0, o_sph_s = 0, o_sph_mat = 0, o_msph = 0, o_rect = 0, o_tri = 0, o_cube = 0, o_obj = 0, o_mat = 0, o_tex = 0,
            o_img = 0, o_perlin = 0;
     size_t o_handle[5] = {0}, o_rank[5] = {0}, o_leaf[5] = {0}, o_sib[5] = {0};
-    int n_objects = 0, n_nodes = 0;
+    int n_objects = 0, n_nodes = 0, n_qnodes = 0, q_object = -1;
 };
 
 // one device's copy of a committed scene
@@ -121,7 +121,7 @@ struct Wavefront {
     cudaStream_t capture_stream = nullptr;         // graphs are captured here (the caller's stream may be the legacy default stream)
     cudaStream_t work_stream = nullptr;            // shim_render_multi renders on it
     struct LoopGraph { cudaGraphExec_t exec; unsigned long long handle; };
-    typedef std::tuple<uint32_t, int, int, int, int, int, int, int, int, int, int, int> GraphKey;
+    typedef std::tuple<uint32_t, int, int, int, int, int, int, int, int, int, int, int, uint32_t> GraphKey;
     std::map<GraphKey, LoopGraph> graphs;          // the whole wavefront loop as one graph (WHILE node), per kernel-variant key
     std::vector<cudaEvent_t> prof;                 // event pairs around the launches of an iteration (SHIM_RENDER_PROFILE)
     std::vector<cudaEvent_t> ev_d2h;
@@ -208,6 +208,7 @@ static int upload_scene(shim::DeviceState* st, int device, DeviceScene** out) {
         v.sibling[i] = (const int*)(base + b.o_sib[i]);
     }
     v.n_objects = b.n_objects; v.n_nodes = b.n_nodes;
+    v.qnodes = b.n_qnodes ? (const QNode*)(base + b.o_qnodes) : nullptr; v.n_qnodes = b.n_qnodes; v.q_object = b.q_object;
     if (st->n_predictors > 0) {  // one open-addressing table per predictor (cleared at the start of every render that uses them)
         const int log2 = st->hrpp_log2;
         d->hrpp_slots_total = ((size_t)1 << log2) * (size_t)st->n_predictors;
@@ -218,6 +219,24 @@ static int upload_scene(shim::DeviceState* st, int device, DeviceScene** out) {
     *out = d.get();
     st->on[device] = std::move(d);
     return SHIM_OK;
+}
+
+// index of the Bvh object of a world that is ONE Bvh among at least one plain object, or -1
+static int single_bvh_object(const FlatScene& f) {
+    int n_bvh = 0, idx = -1;
+    for (size_t i = 0; i < f.objects.size(); ++i) if (f.objects[i].kind == OBJ_BVH) { ++n_bvh; idx = (int)i; }
+    return n_bvh == 1 && f.objects.size() > 1 ? idx : -1;
+}
+// ... and every primitive inside that Bvh is a triangle (the plain objects are rects, no rect sits inside the tree)
+static bool bvh1_triangles_only(const FlatScene& f, int idx) {
+    if (idx < 0 || !f.sph_s.empty() || !f.msph.empty() || !f.cube.empty() || f.tri.empty()) return false;
+    size_t top_rects = 0;
+    for (size_t i = 0; i < f.objects.size(); ++i) {
+        if ((int)i == idx) continue;
+        if (f.objects[i].kind != OBJ_PRIM || prim_type((uint32_t)f.objects[i].ref) != PT_RECT) return false;
+        ++top_rects;
+    }
+    return top_rects * 2 == f.rect.size();
 }
 
 SHIM_API int shim_commit(shim_scene* s) {
@@ -267,6 +286,14 @@ SHIM_API int shim_commit(shim_scene* s) {
         layout(st->smem_signed, s->flat, true);
         if (st->smem_signed.total) s->flat.build_signed_nodes();
     }
+    // a triangle mesh among plain rects (main.rs:791-829): the dense mesh walk reads quantised 32-byte nodes
+    s->flat.qnodes.clear(); s->flat.q_object = -1;
+    {
+        bool media = false;
+        for (const DevObject& o : s->flat.objects) if (o.flags & OBJ_MEDIUM) media = true;
+        const int idx = single_bvh_object(s->flat);
+        if (!media && bvh1_triangles_only(s->flat, idx)) s->flat.build_quantized_nodes(idx);
+    }
     const FlatScene& f = s->flat;
     SceneBlob& b = st->blob;
     auto put = [&](const void* src, size_t bytes) -> size_t {
@@ -277,6 +304,8 @@ SHIM_API int shim_commit(shim_scene* s) {
     };
     b.o_nodes = put(f.nodes.data(), f.nodes.size() * sizeof(DevNode));
     b.o_snodes = put(f.snodes.data(), f.snodes.size() * sizeof(SNode));
+    b.o_qnodes = put(f.qnodes.data(), f.qnodes.size() * sizeof(QNode));
+    b.n_qnodes = (int)f.qnodes.size(); b.q_object = f.q_object;
     b.o_sph = put(f.sph.data(), f.sph.size() * 8); b.o_sph_s = put(f.sph_s.data(), f.sph_s.size() * 16);
     b.o_sph_mat = put(f.sph_mat.data(), f.sph_mat.size() * 4);
     b.o_msph = put(f.msph.data(), f.msph.size() * 16); b.o_rect = put(f.rect.data(), f.rect.size() * 16);
@@ -330,6 +359,7 @@ static int wf_init(Wavefront& w, int device) {
     CU(opt_in_smem(wf_extend<true, false, false, true>, dyn));  CU(opt_in_smem(wf_extend<true, false, true, true>, dyn));
     CU(opt_in_smem(wf_bvh1_walk<true, false>, dyn));  CU(opt_in_smem(wf_bvh1_walk<true, true>, dyn));
     CU(opt_in_smem(wf_bvh1_walk<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI>, dyn));
+    CU(opt_in_smem(wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI, true>, dyn));
     CU(opt_in_smem(wf_extend_list<false, SHIM_LIST_THREADS>, dyn)); CU(opt_in_smem(wf_extend_list<true, SHIM_LIST_THREADS>, dyn));
     CU(opt_in_smem(wf_extend_list<false, SHIM_LIST_THREADS, true>, dyn)); CU(opt_in_smem(wf_extend_list<true, SHIM_LIST_THREADS, true>, dyn));
     CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, false>, dyn));
@@ -356,8 +386,9 @@ static int wf_init(Wavefront& w, int device) {
 
 // environment switches (read per render: the tests and the probes under tools/ force kernel variants with them)
 struct Switches {
-    bool no_trace, no_fuse, no_bvh1, no_smem, no_graph, solo_any, no_solo, no_list, no_bvh1_tri, trace;
+    bool no_trace, no_fuse, no_bvh1, no_smem, no_graph, solo_any, no_solo, no_list, no_bvh1_tri, trace, no_qnodes;
     int tail;   // < 0: default
+    long q_smem_kb;   // < 0: default (SHIM_BVH1_Q_SMEM_KB)
     long pool;  // <= 0: default
     static bool on(const char* name) { return getenv(name) != nullptr; }
     static bool zero(const char* name) { const char* e = getenv(name); return e && atoi(e) == 0; }
@@ -365,6 +396,8 @@ struct Switches {
         no_trace = on("SHIM_NO_TRACE"); no_fuse = on("SHIM_NO_FUSE"); no_bvh1 = on("SHIM_NO_BVH1"); no_smem = on("SHIM_NO_SMEM");
         no_graph = on("SHIM_NO_GRAPH"); solo_any = on("SHIM_SOLO_ANY"); no_solo = zero("SHIM_SOLO"); no_list = zero("SHIM_LIST");
         no_bvh1_tri = zero("SHIM_BVH1_TRI"); trace = on("SHIM_TRACE");
+        no_qnodes = zero("SHIM_QNODES");
+        const char* q = getenv("SHIM_Q_SMEM_KB"); q_smem_kb = q ? atol(q) : -1;
         const char* t = getenv("SHIM_TAIL"); tail = t ? atoi(t) : -1;
         const char* p = getenv("SHIM_POOL_PATHS"); pool = p ? atol(p) : 0;
     }
@@ -375,9 +408,8 @@ static void choose_variant(const shim_scene* s, const shim::DeviceState* st, con
     const FlatScene& f = s->flat;
     k.bvh1_index = -1;
     {   // worlds with exactly one BVH among at least one plain object, no medium, no predictor -> wf_bvh1_list / _walk / _finish
-        int n_bvh = 0, idx = -1;
-        for (size_t i = 0; i < f.objects.size(); ++i) if (f.objects[i].kind == OBJ_BVH) { ++n_bvh; idx = (int)i; }
-        if (n_bvh == 1 && f.objects.size() > 1 && !s->has_media && !k.use_hrpp && !sw.no_bvh1) k.bvh1_index = idx;
+        const int idx = single_bvh_object(f);
+        if (idx >= 0 && !s->has_media && !k.use_hrpp && !sw.no_bvh1) k.bvh1_index = idx;
     }
     k.smem = st->smem;
     const bool use_smem = k.smem.total != 0 && (int)k.smem.total <= w.max_smem - 1024 && !sw.no_smem;
@@ -403,15 +435,19 @@ static void choose_variant(const shim_scene* s, const shim::DeviceState* st, con
             if ((int)i != k.bvh1_index && (f.objects[i].kind != OBJ_PRIM || f.objects[i].flags != 0 || prim_type((uint32_t)f.objects[i].ref) != PT_RECT)) plain_rects = false;
         k.bvh1_list_rects = plain_rects ? 1 : 0;
     }
-    if (k.bvh1_index >= 0 && f.sph_s.empty() && f.msph.empty() && f.cube.empty() && !f.tri.empty() && !sw.no_bvh1_tri) {
-        // plain objects are rects, so every primitive inside the Bvh is a triangle ...
-        bool rects_outside = true;
-        for (size_t i = 0; i < f.objects.size(); ++i)
-            if ((int)i != k.bvh1_index && (f.objects[i].kind != OBJ_PRIM || prim_type((uint32_t)f.objects[i].ref) != PT_RECT)) rects_outside = false;
-        // ... if no rect sits inside it: every rect of the scene is a top-level object
-        size_t top_rects = 0;
-        for (const DevObject& o : f.objects) if (o.kind == OBJ_PRIM) ++top_rects;
-        if (rects_outside && top_rects * 2 == f.rect.size()) k.bvh1_tri_threads = SHIM_BVH1_TRI_THREADS;
+    if (k.bvh1_index >= 0 && !sw.no_bvh1_tri && bvh1_triangles_only(f, k.bvh1_index)) k.bvh1_tri_threads = SHIM_BVH1_TRI_THREADS;
+    // quantised nodes (built at commit for exactly these worlds): the top of the tree in shared memory, as much as fits
+    k.bvh1_q = 0; k.bvh1_q_smem = 0;
+    if (k.bvh1_tri_threads && !k.count_nodes && !f.qnodes.empty() && f.q_object == k.bvh1_index && !sw.no_qnodes) {
+        k.bvh1_q = 1;
+        const long cap_kb = sw.q_smem_kb >= 0 ? sw.q_smem_kb : SHIM_BVH1_Q_SMEM_KB;
+        long cap = cap_kb * 1024L;
+        if (cap > w.max_smem - 2048) cap = w.max_smem - 2048;
+        const size_t fit = cap > 0 ? (size_t)cap / sizeof(QNode) : 0;
+        // all of the tree or none of it: a staged top of a larger tree was measured slower than leaving the whole
+        // shared-memory carve-out to L1 (igea, 267 k triangles: 92.0 ms with the top 160 KB staged, 90.0 ms without);
+        // SHIM_Q_SMEM_KB set explicitly stages the top that fits
+        k.bvh1_q_smem = f.qnodes.size() <= fit ? (uint32_t)f.qnodes.size() : (sw.q_smem_kb >= 0 ? (uint32_t)fit : 0u);
     }
     k.list_threads = 0;
     if (use_smem && !k.count_nodes && !k.use_hrpp && f.nodes.empty() && !k.solo && !sw.no_list) {
@@ -462,7 +498,9 @@ static void launch_extend(const Wavefront& w, const WfParams& k, bool use_smem, 
         else if (k.bvh1_list_rects) wf_bvh1_list<false, true><<<w.grid_stream, 256, 0, st>>>();
         else wf_bvh1_list<false><<<w.grid_stream, 256, 0, st>>>();
         const int wgrid = S ? w.sm_count : w.grid_bvh1_walk;
-        if (k.bvh1_tri_threads && !C) {   // triangle-only tree: no primitive dispatch, more warps
+        if (k.bvh1_q) {   // triangle-only tree on quantised nodes, one block per SM owns the shared-memory top of the tree
+            wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI, true><<<w.sm_count, SHIM_BVH1_TRI_THREADS, k.bvh1_q_smem * (uint32_t)sizeof(QNode), st>>>();
+        } else if (k.bvh1_tri_threads && !C) {   // triangle-only tree: no primitive dispatch, more warps
             if (S) wf_bvh1_walk<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<wgrid, SHIM_BVH1_TRI_THREADS, smem, st>>>();
             else wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<wgrid, SHIM_BVH1_TRI_THREADS, 0, st>>>();
         } else if (S) {
@@ -548,7 +586,8 @@ static bool under_profiler() {
 static int loop_graph(Wavefront& w, const WfParams& k, bool use_smem, Wavefront::LoopGraph* out) {
     // everything launch_iteration branches on (the launches themselves take no arguments)
     const Wavefront::GraphKey key(use_smem ? k.smem.total : 0u, use_smem ? 1 : 0, k.count_nodes != 0, k.has_media != 0, k.use_hrpp != 0,
-                                  k.bvh1_index >= 0 ? 1 + k.bvh1_list_rects : 0, k.bvh1_tri_threads, k.list_threads, k.solo, k.solo_only, k.fused_generate, k.trace_pipeline);
+                                  k.bvh1_index >= 0 ? 1 + k.bvh1_list_rects : 0, k.bvh1_tri_threads, k.list_threads, k.solo, k.solo_only, k.fused_generate, k.trace_pipeline,
+                                  k.bvh1_q ? 1u + k.bvh1_q_smem : 0u);
     auto it = w.graphs.find(key);
     if (it != w.graphs.end()) { *out = it->second; return SHIM_OK; }
     if (!w.capture_stream) CU(cudaStreamCreateWithFlags(&w.capture_stream, cudaStreamNonBlocking));

@@ -53,6 +53,9 @@ SHIM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
+#ifndef SHIM_PHILOX_ROUNDS
+#define SHIM_PHILOX_ROUNDS 10   // experiment builds only: the stream is defined with 10 rounds (oracle, KATs)
+#endif
 struct Rng {
     uint32_t pixel, sample, dim, j, k0, k1;
     uint32_t b0, b1, b2, b3;
@@ -66,7 +69,7 @@ SHIM_HD void rng_key(Rng& r, uint32_t bounce, uint32_t stage) { r.dim = bounce *
 SHIM_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t& o0, uint32_t& o1,
                            uint32_t& o2, uint32_t& o3) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < SHIM_PHILOX_ROUNDS; ++i) {
         uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
         uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
         c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
@@ -182,6 +185,7 @@ struct RayCtx {
     f3 inv_d;   // 1/d with |d| clamped away from 0 so that the products below stay finite
     f3 o_inv;   // -o * inv_d: a slab plane distance is one fma(plane, inv_d, o_inv)
     int soff[3]; // SNode walks: byte offset of the ray's {near_l, near_r, far_l, far_r} planes of axis k inside a node
+    uint32_t qrot[3]; // QNode walks: rotation (0 / 16 bits) that brings the plane bytes of axis k into that order
 };
 SHIM_HD f3 rot_y(f3 v, float s, float c) { return mk3(c * v.x - s * v.z, v.y, s * v.x + c * v.z); }       // instance.rs:104-110
 SHIM_HD f3 rot_y_back(f3 v, float s, float c) { return mk3(c * v.x + s * v.z, v.y, -s * v.x + c * v.z); } // instance.rs:125-134
@@ -204,6 +208,9 @@ SHIM_HD void make_ctx(RayCtx& c, const Ray& r) {
     c.soff[0] = signbit_f(c.inv_d.x) ? 16 : 0;
     c.soff[1] = signbit_f(c.inv_d.y) ? 48 : 32;
     c.soff[2] = signbit_f(c.inv_d.z) ? 80 : 64;
+    c.qrot[0] = signbit_f(c.inv_d.x) ? 16u : 0u;
+    c.qrot[1] = signbit_f(c.inv_d.y) ? 16u : 0u;
+    c.qrot[2] = signbit_f(c.inv_d.z) ? 16u : 0u;
 }
 
 struct TraceCounters { uint32_t nodes, prims, hrpp_tp, hrpp_fp, hrpp_none; };
@@ -360,6 +367,24 @@ SHIM_HD bool slab(float mnx, float mny, float mnz, float mxx, float mxy, float m
 
 struct BvhBest { float t; uint32_t prim; int face; bool any; };
 
+// One 64-byte DevNode.  A divergent walk out of global memory is bound by the L1 data pipe (one wavefront per lane and
+// load instruction: 74 % of its peak in the mesh walk with four 16-byte loads per node), so a node in global memory is
+// fetched with two 32-byte loads (LDG.E.ENL2.256, sm_100a) - half the wavefronts.  Nodes staged in shared memory keep
+// the 16-byte loads.
+SHIM_HD void load_node(const DevNode* nodes, int cur, f4& a, f4& b, f4& c, i4& d) {
+    const DevNode* n = nodes + cur;
+#if defined(__CUDA_ARCH__) && !defined(SHIM_NO_LDG256)
+    if (__isGlobal(nodes)) {
+        asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(n));
+        asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8+32];"
+            : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w), "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(n));
+        return;
+    }
+#endif
+    a = n->a; b = n->b; c = n->c; d = n->d;
+}
+
 #define SHIM_BVH_STACK 40
 // An exact f32 tie between two primitives of one BVH (bvh.rs:396-415).  Across leaves the reference compares the two
 // f32 t's and the later leaf wins.  Inside one recorded two-primitive leaf it tests the right child against the LEFT
@@ -388,11 +413,66 @@ SHIM_HD void slab_pair_signed(const f4& X, const f4& Y, const f4& Z, const RayCt
     hl = !(fl < tl);   // aabb.rs:36 rejects only when t_max < t_min
     hr = !(fr < tr);
 }
-// SIGNED: walk sv.snodes (SNode, see shim_types.h); start_node and every non-negative reference are then byte offsets.
+// ---- QNode (shim_types.h): the eight words of a node and the slab test of both child boxes on the quantised planes
+SHIM_HD uint32_t byte_perm32(uint32_t x, uint32_t y, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, sel);
+#else
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
+SHIM_HD uint32_t rotl32(uint32_t w, uint32_t r) {   // r = 0 or 16
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(w, w, r);
+#else
+    return r ? ((w << r) | (w >> (32u - r))) : w;
+#endif
+}
+SHIM_HD void load_qnode(const QNode* nodes, int cur, uint32_t* w) {
+    const QNode* n = nodes + cur;
+#if defined(__CUDA_ARCH__)
+    if (__isGlobal(nodes)) {
+        asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(n));
+        return;
+    }
+#endif
+    w[0] = n->o[0]; w[1] = n->o[1]; w[2] = n->o[2]; w[3] = n->q[0]; w[4] = n->q[1]; w[5] = n->q[2];
+    w[6] = (uint32_t)n->left; w[7] = (uint32_t)n->right;
+}
+// A plane is origin + q * S.  With f = the float 1 + q * 2^-15 (the byte dropped into the mantissa of 1.0 by one PRMT)
+// and a = 2^15 * S / d:  (origin + q * S - o) / d  =  f * a + ((origin - o) / d - a): two instructions per plane.
+// The rounding of these f32 operations is far below the grid step the builder added as margin (2^-9 of a step for
+// the cancellation in b; an ulp of the distances otherwise, as in slab()).
+SHIM_HD void slab_pair_q(const uint32_t* w, const RayCtx& c, float t_min, float t_cull, float& tl, float& tr, bool& hl, bool& hr) {
+    float nl[3], nr[3], fl[3], fr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float inv = k == 0 ? c.inv_d.x : (k == 1 ? c.inv_d.y : c.inv_d.z), oinv = k == 0 ? c.o_inv.x : (k == 1 ? c.o_inv.y : c.o_inv.z);
+        const float a = i2f((int)((w[k] & 0xffu) << 23)) * inv;
+        const float b = slab_plane(i2f((int)w[k]), inv, oinv) - a;
+        const uint32_t q = rotl32(w[3 + k], c.qrot[k]);   // bytes {near_l, near_r, far_l, far_r}
+        nl[k] = slab_plane(i2f((int)byte_perm32(q, 0x3F800000u, 0x7604u)), a, b);
+        nr[k] = slab_plane(i2f((int)byte_perm32(q, 0x3F800000u, 0x7614u)), a, b);
+        fl[k] = slab_plane(i2f((int)byte_perm32(q, 0x3F800000u, 0x7624u)), a, b);
+        fr[k] = slab_plane(i2f((int)byte_perm32(q, 0x3F800000u, 0x7634u)), a, b);
+    }
+    tl = fmaxf(max3f(nl[0], nl[1], nl[2]), t_min);
+    tr = fmaxf(max3f(nr[0], nr[1], nr[2]), t_min);
+    const float el = fminf(min3f(fl[0], fl[1], fl[2]), t_cull);
+    const float er = fminf(min3f(fr[0], fr[1], fr[2]), t_cull);
+    hl = !(el < tl);
+    hr = !(er < tr);
+}
+// SIGNED: node layout.  1 = walk sv.snodes (SNode, see shim_types.h); start_node and every non-negative reference are
+// then byte offsets.  2 = walk sv.qnodes (QNode: larger boxes, so more nodes may be visited; the hit is the same).
 // Both layouts visit the same nodes in the same order and return the same hit: for a box with min <= max and a finite
 // reciprocal the plane the sign picks IS the smaller of the two products (fma is monotonic), and max/min are
 // associative.
-template <bool COUNT, int ONLY = -1, bool SIGNED = false>
+template <bool COUNT, int ONLY = -1, int SIGNED = 0>
 SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, float t_min, float t_max, BvhBest& best,
                          TraceCounters* cnt) {
     best.t = t_max; best.prim = 0; best.face = 0; best.any = false;
@@ -406,7 +486,7 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
     int cur = start_node;  // >= 0 inner node, < 0 ~prim_ref, SHIM_STACK_END when done
 #if defined(__CUDA_ARCH__)
     uint32_t p0 = 0, px = 0, py = 0, pz = 0;
-    if (SIGNED) {   // the SNode walk lives in shared memory (wf_extend_solo / wf_trace_solo stage sv.snodes there)
+    if (SIGNED == 1) {   // the SNode walk lives in shared memory (wf_extend_solo / wf_trace_solo stage sv.snodes there)
         p0 = (uint32_t)__cvta_generic_to_shared(sv.snodes);
         px = p0 + (uint32_t)c.soff[0]; py = p0 + (uint32_t)c.soff[1]; pz = p0 + (uint32_t)c.soff[2];
         // opaque to the optimiser: otherwise it re-derives the three offsets from the direction signs in every
@@ -419,7 +499,13 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
             float tl, tr;
             bool hl, hr;
             int left, right;
-            if (SIGNED) {
+            if (SIGNED == 2) {
+                uint32_t w[8];
+                load_qnode(sv.qnodes, cur, w);
+                slab_pair_q(w, c, t_min, t_cull, tl, tr, hl, hr);
+                left = (int)w[6]; right = (int)w[7];
+                hr = hr && right != CHILD_NONE;
+            } else if (SIGNED == 1) {
                 f4 X, Y, Z;
                 i4 nd;
 #if defined(__CUDA_ARCH__)
@@ -439,9 +525,9 @@ SHIM_HD bool bvh_closest(const SceneView& sv, int start_node, const RayCtx& c, f
                 hr = hr && nd.y != CHILD_NONE;
                 left = nd.x; right = nd.y;
             } else {
-                const DevNode& n = sv.nodes[cur];
-                f4 na = n.a, nb = n.b, nc = n.c;
-                i4 nd = n.d;
+                f4 na, nb, nc;
+                i4 nd;
+                load_node(sv.nodes, cur, na, nb, nc, nd);
                 hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, t_min, t_cull, tl);
                 hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, t_min, t_cull, tr);
                 hr = hr && nd.y != CHILD_NONE;
@@ -592,7 +678,8 @@ SHIM_HD bool bvh_closest_predicted(const SceneView& sv, const DevObject& ob, con
 
 // shape of one top-level object against its object-space ray
 // HASBVH = false: the caller knows the world holds no Bvh object (a flat list like the Cornell scenes)
-template <bool COUNT, bool HRPP, bool HASBVH = true>
+// QN: the Bvh object sv.q_object is walked on its quantised nodes (same hit; tests/hostsim pins that)
+template <bool COUNT, bool HRPP, bool HASBVH = true, bool QN = false>
 SHIM_HD bool shape_hit(const SceneView& sv, const DevObject& ob, const RayCtx& c, float t_min, float t_max, float& t, uint32_t& prim,
                        int& face, TraceCounters* cnt) {
     if (!HASBVH || ob.kind == OBJ_PRIM) {
@@ -602,15 +689,17 @@ SHIM_HD bool shape_hit(const SceneView& sv, const DevObject& ob, const RayCtx& c
         return false;
     }
     BvhBest best;
-    bool hit = (HRPP && (ob.flags & OBJ_PREDICTOR)) ? bvh_closest_predicted<COUNT>(sv, ob, c, t_min, t_max, best, cnt)
-                                                     : bvh_closest<COUNT>(sv, ob.ref, c, t_min, t_max, best, cnt);
+    bool hit;
+    if (QN && sv.qnodes && ob.ref == sv.objects[sv.q_object].ref) hit = bvh_closest<COUNT, -1, 2>(sv, 0, c, t_min, t_max, best, cnt);
+    else hit = (HRPP && (ob.flags & OBJ_PREDICTOR)) ? bvh_closest_predicted<COUNT>(sv, ob, c, t_min, t_max, best, cnt)
+                                                    : bvh_closest<COUNT>(sv, ob.ref, c, t_min, t_max, best, cnt);
     if (hit) { t = best.t; prim = best.prim; face = best.face; return true; }
     return false;
 }
 
 // HittableList::hit over the flattened world (hittable.rs:100-118), with ConstantMedium::hit
 // (hittable.rs:177-233) for medium objects.  `rng` must be keyed to STAGE_INTERSECT.
-template <bool COUNT, bool HRPP = false, bool HASBVH = true>
+template <bool COUNT, bool HRPP = false, bool HASBVH = true, bool QN = false>
 SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float t_max, Rng& rng, TraceCounters* cnt) {
     Hit h; h.t = t_max; h.obj = -1; h.prim = 0; h.face = 0;
     float closest = t_max;
@@ -622,8 +711,8 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
         float t; uint32_t prim; int face;
         if (ob.flags & OBJ_MEDIUM) {
             float t1, t2;
-            if (!shape_hit<COUNT, HRPP, HASBVH>(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, cnt)) continue;
-            if (!shape_hit<COUNT, HRPP, HASBVH>(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, cnt)) continue;
+            if (!shape_hit<COUNT, HRPP, HASBVH, QN>(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, cnt)) continue;
+            if (!shape_hit<COUNT, HRPP, HASBVH, QN>(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, cnt)) continue;
             if (t1 < t_min) t1 = t_min;
             if (t2 > closest) t2 = closest;
             if (t1 >= t2) continue;
@@ -635,7 +724,7 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
             t = t1 + hit_distance / ray_length;
             closest = t;
             h.t = t; h.obj = oi; h.prim = 0; h.face = 0;
-        } else if (shape_hit<COUNT, HRPP, HASBVH>(sv, ob, c, t_min, closest, t, prim, face, cnt)) {
+        } else if (shape_hit<COUNT, HRPP, HASBVH, QN>(sv, ob, c, t_min, closest, t, prim, face, cnt)) {
             closest = t;
             h.t = t; h.obj = oi; h.prim = prim; h.face = face;
         }

@@ -83,6 +83,8 @@ struct WfParams {
     int solo_only;    // wf_extend_solo: the one primitive type of the Bvh (PT_*), or -1 when mixed
     int solo;         // > 0: the world is exactly one plain Bvh: wf_extend_solo with this many threads per block
     int bvh1_index;   // >= 0: the world is one BVH object (this one) among plain primitives, no medium: the wf_bvh1_* kernels apply
+    uint32_t bvh1_q_smem;  // wf_bvh1_walk on quantised nodes (sv.qnodes): how many of them (the top of the tree) sit in shared memory; 0 with bvh1_q = 0
+    int bvh1_q;            // the mesh walk uses the QNode layout
     i4* bvh1_hit;          // one-Bvh worlds: closest-hit record per queued ray (wf_bvh1_list / _walk / _finish)
     uint32_t* bvh1_queue;  // ... rays that can reach the tree
     SmemLayout smem;
@@ -390,6 +392,9 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_list() {
 #ifndef SHIM_BVH1_REFILL_IDLE
 #define SHIM_BVH1_REFILL_IDLE 12
 #endif
+#ifndef SHIM_BVH1_Q_SMEM_KB
+#define SHIM_BVH1_Q_SMEM_KB 200   // a quantised tree up to this size (6400 nodes) is staged in shared memory whole
+#endif
 enum { BVH1_NONE = 0xffff, BVH1_DROP = 0xfffe };   // obj field of a record: no hit / path ends without a contribution
 // record: x = t bits, y = obj | face << 16 | post << 24 (post: the list hit comes after the Bvh in list order), z = prim_ref
 
@@ -510,7 +515,10 @@ __global__ void __launch_bounds__(256) wf_bvh1_list() {
 #ifndef SHIM_BVH1_PRIM_BATCH
 #define SHIM_BVH1_PRIM_BATCH 8
 #endif
-template <bool SMEM, bool COUNT, int THREADS = SHIM_EXTEND_THREADS, int ONLY = -1>
+// QN: the tree is walked on its quantised 32-byte nodes (QNode, breadth-first order): the first p.bvh1_q_smem of them -
+// the top of the tree, or all of it - are staged in shared memory by bulk copies, the rest is fetched with one 32-byte
+// load per node.  (SMEM and QN exclude each other.)
+template <bool SMEM, bool COUNT, int THREADS = SHIM_EXTEND_THREADS, int ONLY = -1, bool QN = false>
 __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
     const WfParams& p = g_p;
     const int cur_q = (int)p.cnt[CNT_CUR];
@@ -519,6 +527,19 @@ __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const SceneView sv = SMEM ? stage_scene(p, smem, &bar) : p.sv;
+    const uint32_t q_smem = p.bvh1_q_smem;   // 0 unless QN
+    if (QN && q_smem) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = q_smem * (uint32_t)sizeof(QNode);
+            mbar_expect_tx(&bar, bytes);
+            for (uint32_t off = 0; off < bytes; off += 32768u)
+                bulk_g2s(smem + off, reinterpret_cast<const unsigned char*>(p.sv.qnodes) + off, bytes - off < 32768u ? bytes - off : 32768u, &bar);
+        }
+        mbar_wait(&bar, 0);
+    }
+    const uint32_t q_base = smem_u32(smem);
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const int bo = p.bvh1_index;
     const DevObject& bob = sv.objects[bo];
@@ -554,7 +575,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
                 Ray r; r.o = mk3(o.x, o.y, o.z); r.d = mk3(d.x, d.y, d.z); r.time = o.w;
                 make_ctx(c, object_ray(bob, r));
                 best.t = list_t; best.prim = 0; best.face = 0; best.any = false;
-                t_cull = list_t; sp = 0; cur = bob.ref;
+                t_cull = list_t; sp = 0; cur = QN ? 0 : bob.ref;
                 active = true;
             }
             if (got + n_idle >= count) more = false;
@@ -569,13 +590,28 @@ __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
                 const unsigned pm = __ballot_sync(0xffffffffu, active && cur < 0);
                 if (__popc(pm) >= SHIM_BVH1_PRIM_BATCH) break;
                 if (at_node) {
-                    const DevNode& nd = sv.nodes[cur];
-                    f4 na = nd.a, nb = nd.b, nc = nd.c;
-                    i4 ch = nd.d;
-                    if (COUNT) nodes++;
+                    i4 ch;
                     float tl, tr;
-                    bool hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, 0.001f, t_cull, tl);
-                    bool hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, 0.001f, t_cull, tr);
+                    bool hl, hr;
+                    if (COUNT) nodes++;
+                    if (QN) {
+                        uint32_t w[8];
+                        if ((uint32_t)cur < q_smem) {
+                            const uint32_t a = q_base + (uint32_t)cur * (uint32_t)sizeof(QNode);
+                            asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
+                            asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+16];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(a));
+                        } else {
+                            asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(sv.qnodes + cur));
+                        }
+                        slab_pair_q(w, c, 0.001f, t_cull, tl, tr, hl, hr);
+                        ch.x = (int)w[6]; ch.y = (int)w[7];
+                    } else {
+                        f4 na, nb, nc;
+                        load_node(sv.nodes, cur, na, nb, nc, ch);
+                        hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, 0.001f, t_cull, tl);
+                        hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, 0.001f, t_cull, tr);
+                    }
                     hr = hr && ch.y != CHILD_NONE;
                     if (hl && hr) {
                         bool swap = tr < tl;
@@ -1022,7 +1058,9 @@ __global__ void __launch_bounds__(256) trace_closest_kernel(SceneView sv, const 
         rng_init(rng, (uint32_t)i, 0, seed);
         rng_key(rng, 0, STAGE_INTERSECT);
         TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
-        Hit h = counters ? closest_hit<true>(sv, r, t_min, t_max, rng, &tc) : closest_hit<false>(sv, r, t_min, t_max, rng, &tc);
+        // a scene with quantised nodes is queried on them (what its renders walk), unless node visits are being counted
+        Hit h = counters ? closest_hit<true>(sv, r, t_min, t_max, rng, &tc)
+                         : (sv.qnodes ? closest_hit<false, false, true, true>(sv, r, t_min, t_max, rng, &tc) : closest_hit<false>(sv, r, t_min, t_max, rng, &tc));
         nodes += tc.nodes; prims += tc.prims;
         prim_id[i] = hit_handle(sv, h);
         t_out[i] = h.obj < 0 ? SHIM_INF : h.t;

@@ -592,6 +592,7 @@ SceneView FlatScene::view() const {
     v.images = images.data(); v.perlin = perlin.data();
     for (int i = 0; i < 5; ++i) { v.handle[i] = handle[i].data(); v.rank[i] = rank[i].data(); v.leaf[i] = leaf[i].data(); v.sibling[i] = sibling[i].data(); }
     v.n_objects = (int)objects.size(); v.n_nodes = (int)nodes.size();
+    v.qnodes = qnodes.empty() ? nullptr : qnodes.data(); v.n_qnodes = (int)qnodes.size(); v.q_object = q_object;
     return v;
 }
 // DevNode -> SNode (shim_types.h): the planes of each axis in both orders, child node references as byte offsets
@@ -610,8 +611,77 @@ void FlatScene::build_signed_nodes() {
     }
 }
 
+// DevNode -> QNode (shim_types.h) for the tree of object `oi`, renumbered breadth-first.  Everything is rounded
+// outwards in exact (double) arithmetic against the very float the device decodes, plus one grid step of margin for
+// the device's own f32 rounding of the plane distances.
+namespace {
+uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+float bits_f32(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+// grid of one axis for planes in [lo, hi]: origin bits (low byte = exponent byte of 2^15 * step) and the step
+bool qgrid(float lo, float hi, uint32_t& o_bits, double& origin, double& step) {
+    if (!std::isfinite(lo) || !std::isfinite(hi) || std::fabs(lo) > 4096.0f || std::fabs(hi) > 4096.0f || hi < lo) return false;
+    const double ext = (double)hi - (double)lo;
+    int s = ext > 0.0 ? (int)std::ceil(std::log2(ext / 252.0)) : std::ilogb(std::fmax(std::fabs((double)lo), 1e-30)) - 20;
+    if (s < -126) s = -126;
+    for (;; ++s) {
+        const int E = s + 15 + 127;
+        if (E < 1) continue;
+        if (E > 254) return false;
+        const double S = std::ldexp(1.0, s);
+        const double x = (double)lo - S;   // one step below the lowest plane
+        float xf = (float)x;
+        if ((double)xf > x) xf = std::nextafterf(xf, -INFINITY);
+        uint32_t b = (f32_bits(xf) & ~0xffu) | (uint32_t)E;
+        if ((double)bits_f32(b) > x) {      // the exponent byte moved the value up: one 256-ulp step towards -inf
+            if (b & 0x80000000u) b += 256u;
+            else if (b >= 512u) b -= 256u;
+            else b = 0x80000000u | (uint32_t)E;   // below the smallest positive grid value: a negative denormal
+        }
+        const double o = (double)bits_f32(b);
+        if (!(o <= x) || !std::isfinite(o)) continue;
+        if (std::ceil(((double)hi - o) / S) + 1.0 > 255.0) continue;
+        o_bits = b; origin = o; step = S;
+        return true;
+    }
+}
+}  // namespace
+bool FlatScene::build_quantized_nodes(int oi) {
+    qnodes.clear();
+    q_object = -1;
+    if (oi < 0 || oi >= (int)objects.size() || objects[oi].kind != OBJ_BVH) return false;
+    std::vector<int> order{objects[oi].ref};   // QNode index -> DevNode index, breadth-first
+    std::unordered_map<int, int> qindex{{objects[oi].ref, 0}};
+    for (size_t h = 0; h < order.size(); ++h) {
+        const DevNode& n = nodes[order[h]];
+        for (int c : {n.d.x, n.d.y})
+            if (c >= 0) { qindex[c] = (int)order.size(); order.push_back(c); }
+    }
+    std::vector<QNode> out(order.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+        const DevNode& n = nodes[order[i]];
+        const bool has_r = n.d.y != CHILD_NONE;
+        const float lmn[3] = {n.a.x, n.a.y, n.a.z}, lmx[3] = {n.a.w, n.b.x, n.b.y};
+        const float rmn[3] = {n.b.z, n.b.w, n.c.x}, rmx[3] = {n.c.y, n.c.z, n.c.w};
+        QNode& q = out[i];
+        for (int k = 0; k < 3; ++k) {
+            const float lo = has_r ? std::fmin(lmn[k], rmn[k]) : lmn[k], hi = has_r ? std::fmax(lmx[k], rmx[k]) : lmx[k];
+            double origin, S;
+            if (!qgrid(lo, hi, q.o[k], origin, S)) return false;
+            auto down = [&](float v) { return (uint32_t)(std::floor(((double)v - origin) / S) - 1.0); };
+            auto up = [&](float v) { return (uint32_t)(std::ceil(((double)v - origin) / S) + 1.0); };
+            if (!(lmn[k] <= lmx[k]) || (has_r && !(rmn[k] <= rmx[k]))) return false;
+            q.q[k] = down(lmn[k]) | (has_r ? down(rmn[k]) : 255u) << 8 | up(lmx[k]) << 16 | (has_r ? up(rmx[k]) : 0u) << 24;
+        }
+        q.left = n.d.x >= 0 ? qindex[n.d.x] : n.d.x;
+        q.right = n.d.y >= 0 ? qindex[n.d.y] : n.d.y;
+    }
+    qnodes.swap(out);
+    q_object = oi;
+    return true;
+}
+
 uint64_t FlatScene::bytes() const {
-    uint64_t b = nodes.size() * sizeof(DevNode) + snodes.size() * sizeof(SNode) + sph.size() * 8 + sph_s.size() * 16 + sph_mat.size() * 4 +
+    uint64_t b = nodes.size() * sizeof(DevNode) + snodes.size() * sizeof(SNode) + qnodes.size() * sizeof(QNode) + sph.size() * 8 + sph_s.size() * 16 + sph_mat.size() * 4 +
                  (msph.size() + rect.size() + tri.size() + cube.size() + materials.size() + textures.size()) * 16 +
                  objects.size() * sizeof(DevObject) + images.size() + perlin.size();
     for (int i = 0; i < 5; ++i) b += handle[i].size() * 16;

@@ -49,6 +49,9 @@ struct FlatScene {
     std::vector<DevNode> nodes;
     std::vector<SNode> snodes;       // `nodes` in the signed layout (build_signed_nodes; empty = not built)
     void build_signed_nodes();
+    std::vector<QNode> qnodes;       // the tree of object q_object quantised (build_quantized_nodes; empty = not built)
+    int q_object = -1;
+    bool build_quantized_nodes(int object_index);   // false: not representable (left empty)
     std::vector<double> sph;
     std::vector<f4> sph_s;
     std::vector<int> sph_mat;

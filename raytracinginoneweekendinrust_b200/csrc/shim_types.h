@@ -80,6 +80,22 @@ struct alignas(16) SNode {
     i4 d;      // left ref, right ref, parent (node index), unused
 };
 
+// The node once more, quantised to 32 bytes, for the dense mesh walk (wf_bvh1_walk): one 32-byte fetch (LDG.256, or two
+// LDS.128 for the top of the tree staged in shared memory) decides both descents, the node array is half as large (cache
+// hit rates, a 4.9 k-triangle tree fits shared memory whole).  Per axis a grid origin o and a power-of-two step S; a
+// child plane is o + q * S with an 8-bit q, rounded OUTWARDS by at least one step, so the decoded boxes contain the
+// exact ones (a walk over larger boxes visits more candidates and returns the same hit, see bvh_closest).
+//   o[k]   f32 bits of the origin; its low mantissa byte doubles as the IEEE exponent byte of 2^15 * S (the origin is
+//          the float those 32 bits spell, exponent byte included: the builder quantises against exactly that value)
+//   q[k]   bytes {l.min, r.min, l.max, r.max}; an empty child slot is {.., 255, .., 0}: never hit
+//   left/right   >= 0 index into the QNode array (breadth-first order, root = 0: the first K nodes are the top of the
+//          tree), < 0 ~prim_ref, CHILD_NONE
+struct alignas(32) QNode {
+    uint32_t o[3];
+    uint32_t q[3];
+    int left, right;
+};
+
 enum ObjFlags { OBJ_TRANSLATE = 1, OBJ_ROTATE = 2, OBJ_MEDIUM = 4, OBJ_PREDICTOR = 8 };
 enum ObjKind { OBJ_PRIM = 0, OBJ_BVH = 1 };
 
@@ -121,6 +137,9 @@ struct SceneView {
     struct HrppSlot* hrpp_slots;
     uint32_t hrpp_mask;
     int hrpp_log2;
+    // quantised nodes of ONE Bvh object (q_object; the mesh of a one-Bvh-among-plain-objects world), or null
+    const QNode* qnodes;
+    int n_qnodes, q_object;
 };
 enum { HRPP_LEAVES = 4, HRPP_PROBES = 8 };
 // One predictor slot = one 32-byte sector: the tagged 48-bit key and up to HRPP_LEAVES predicted leaf nodes, so a

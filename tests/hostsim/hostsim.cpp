@@ -108,6 +108,38 @@ extern "C" __attribute__((visibility("default"))) int hs_trace_closest_solo(shim
     return 0;
 }
 
+// closest hit of a world with ONE Bvh object among plain objects, the Bvh walked on its quantised nodes (QNode, what
+// wf_bvh1_walk reads): must equal the walk over the exact boxes in id and t; returns the number of QNodes or -1
+extern "C" __attribute__((visibility("default"))) int hs_trace_closest_q(shim_scene* s, const float* rays, int64_t n, float t_min,
+                                                                        float t_max, int32_t* prim, float* t, uint64_t* counters) {
+    int idx = -1, n_bvh = 0;
+    for (size_t i = 0; i < s->flat.objects.size(); ++i) if (s->flat.objects[i].kind == OBJ_BVH) { ++n_bvh; idx = (int)i; }
+    if (n_bvh != 1) return -1;
+    if (s->flat.q_object != idx && !s->flat.build_quantized_nodes(idx)) return -1;
+    SceneView sv = view_of(s);
+    uint64_t nodes = 0, prims = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* q = rays + i * 7;
+        Ray r; r.o = mk3(q[0], q[1], q[2]); r.d = mk3(q[3], q[4], q[5]); r.time = q[6];
+        Rng rng;
+        rng_init(rng, (uint32_t)i, 0, 0);
+        rng_key(rng, 0, STAGE_INTERSECT);
+        TraceCounters tc; tc.nodes = 0; tc.prims = 0; tc.hrpp_tp = 0; tc.hrpp_fp = 0; tc.hrpp_none = 0;
+        Hit h = closest_hit<true, false, true, true>(sv, r, t_min, t_max, rng, &tc);
+        nodes += tc.nodes; prims += tc.prims;
+        prim[i] = hit_handle(sv, h);
+        t[i] = h.obj < 0 ? INFINITY : h.t;
+    }
+    if (counters) { counters[0] = (uint64_t)n; counters[1] = nodes; counters[2] = prims; }
+    return (int)s->flat.qnodes.size();
+}
+// the QNode array (8 words per node) for inspection
+extern "C" __attribute__((visibility("default"))) int hs_qnodes(shim_scene* s, uint32_t* out, int max_nodes) {
+    int n = (int)s->flat.qnodes.size();
+    if (out) memcpy(out, s->flat.qnodes.data(), sizeof(QNode) * (size_t)(n < max_nodes ? n : max_nodes));
+    return n;
+}
+
 // the wavefront's per-path arithmetic, executed path by path (same order of operations as
 // wf_generate / wf_extend / wf_shade)
 extern "C" __attribute__((visibility("default"))) int hs_sample_radiance(shim_scene* s, const shim_camera* cam,

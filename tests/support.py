@@ -96,6 +96,10 @@ def hostsim_lib():
         lib.hs_commit.argtypes = [_P]
         lib.hs_trace_closest.restype = _I
         lib.hs_trace_closest.argtypes = [_P, _P, C.c_int64, _F, _F, C.c_uint64, _P, _P, _P]
+        lib.hs_trace_closest_q.restype = _I
+        lib.hs_trace_closest_q.argtypes = [_P, _P, C.c_int64, _F, _F, _P, _P, _P]
+        lib.hs_qnodes.restype = _I
+        lib.hs_qnodes.argtypes = [_P, _P, _I]
         lib.hs_trace_closest_solo.restype = _I
         lib.hs_trace_closest_solo.argtypes = [_P, _P, C.c_int64, _F, _F, _I, _P, _P, _P]
         lib.hs_sample_radiance.restype = _I
@@ -190,6 +194,15 @@ class HostSimScene(capi.SceneHandle):
                                             t.ctypes.data, cnt.ctypes.data)
         assert rc == 0, "not a one-Bvh world"
         return prim, t, cnt
+
+    def trace_closest_q(self, rays, t_min=0.001, t_max=float("inf")):
+        """closest hit with the one Bvh object walked on its quantised nodes (QNode); returns ids, t, counters, node count."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 7)
+        n = rays.shape[0]
+        prim = np.empty(n, np.int32); t = np.empty(n, np.float32); cnt = np.zeros(3, np.uint64)
+        nq = self.lib.hs_trace_closest_q(self.ptr, rays.ctypes.data, n, t_min, t_max, prim.ctypes.data, t.ctypes.data, cnt.ctypes.data)
+        assert nq > 0, "no quantised nodes (not a one-Bvh world, or not representable)"
+        return prim, t, cnt, nq
 
     def enable_predictors(self, log2=16):
         return self.lib.hs_enable_predictors(self.ptr, log2)

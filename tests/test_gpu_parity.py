@@ -150,6 +150,25 @@ def test_kernel_variants_agree():
         np.testing.assert_allclose(img, ref, rtol=2e-5, atol=2e-6, err_msg=str(env))
 
 
+def test_mesh_walk_variants_agree():
+    """A triangle mesh among the Cornell rects (main.rs:791-829): the dense walk on quantised 32-byte nodes with the whole
+    tree staged in shared memory (default), with only its top staged, with none staged, on the exact 64-byte nodes, the
+    mixed-primitive walk and the generic closest-hit kernel trace the same rays and give the oracle's image."""
+    g, o, info = build_pair("bunny")
+    cam = CAMERAS["bunny"]
+    W, H, spp = 160, 120, 6
+    p = api.make_params(W, H, spp, 50, background=info.background, seed=7)
+    ref, st = g.render(cam, p)
+    assert st.extend_variant == 1                  # wf_bvh1_list / _walk / _finish
+    want, _ = o.render(cam, o.params(W, H, spp, 50, background=info.background, seed=7, iterative=True))
+    np.testing.assert_allclose(ref, want, rtol=2e-5, atol=2e-6)
+    for env in ({"SHIM_Q_SMEM_KB": "32"}, {"SHIM_Q_SMEM_KB": "0"}, {"SHIM_QNODES": "0"}, {"SHIM_BVH1_TRI": "0"},
+                {"SHIM_NO_BVH1": "1"}, {"SHIM_NO_GRAPH": "1"}, {"SHIM_NO_GRAPH": "1", "SHIM_Q_SMEM_KB": "0"}):
+        img, st2 = _render_with_env(g, cam, p, env)
+        assert st2.rays == st.rays, env
+        np.testing.assert_allclose(img, ref, rtol=2e-5, atol=2e-6, err_msg=str(env))
+
+
 def test_page_locked_framebuffer_path_matches_staged_path():
     g, o, info = build_pair("cornell-smoke")
     cam = CAMERAS["cornell-smoke"]

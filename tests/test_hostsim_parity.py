@@ -114,3 +114,36 @@ def test_signed_node_layout_walks_the_same_nodes(name, reference_tree):
     np.testing.assert_array_equal(p_ref, p1)
     hit = p_ref >= 0
     np.testing.assert_array_equal(t_ref[hit].view(np.uint32), t1[hit].view(np.uint32))
+
+
+@pytest.mark.parametrize("name,kw", [("bunny", {}), ("bunny", {"material": "dielectric"}), ("igea-hrpp", {"n_tris": 20000, "predictor": False}),
+                                     ("gargoyle", {})])
+def test_quantised_nodes_return_the_same_hits(name, kw):
+    """The 32-byte quantised node layout of the mesh walk (QNode, shim_types.h: 8-bit child planes on a power-of-two
+    grid, rounded outwards) against the exact 64-byte nodes and the oracle: same ids, bit-equal t on the integrator's
+    own rays, on zero-component / axis-parallel rays and on rays that start on the mesh.  The boxes are larger, so the
+    walk may visit more nodes - the margin is checked to stay small."""
+    kw = dict(T.SMALL.get(name, {}), **kw)
+    o, h = support.OracleScene(), support.HostSimScene()
+    info = scenes.build(o, name, seed=1, **kw)
+    scenes.build(h, name, seed=1, **kw)
+    cam = T.CAMERAS[name]
+    W, H, spp = 160, 120, 4
+    po = o.params(W, H, spp, 50, background=info.background, seed=5, iterative=True)
+    rays = o.record_path_rays(cam, po, support.random_xys(W, H, spp, 4000, seed=9), 60000)
+    rs = np.random.RandomState(4)
+    axis = rays[:3000].copy()
+    for i in range(len(axis)):
+        k = rs.randint(0, 3)
+        axis[i, 3 + k] = [0.0, -0.0][rs.randint(0, 2)]
+        if rs.rand() < 0.3:
+            axis[i, 3 + (k + 1) % 3] = [0.0, -0.0][rs.randint(0, 2)]
+    rays = np.concatenate([rays, axis])
+    p0, t0, c0 = h.trace_closest(rays, counters=True)
+    p1, t1, c1, nq = h.trace_closest_q(rays)
+    np.testing.assert_array_equal(p0, p1)
+    np.testing.assert_array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    p_ref, t_ref = o.trace_closest(rays, seed=0)
+    np.testing.assert_array_equal(p_ref, p1)
+    assert nq > 0 and c1[1] >= c0[1] * 0.999          # larger boxes: never fewer node visits (up to the near/far order)
+    assert c1[1] <= c0[1] * 1.25, (c0, c1)             # ... and not many more
