@@ -119,6 +119,30 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred) {
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
 
+// Block-wide appends for the streaming kernels (256-thread blocks, several per SM).  One atomic per warp and queue on
+// a handful of global counters was what these kernels waited for (ncu: 57 % of wf_bvh1_list's and 45 % of
+// wf_bvh1_finish's stall samples sat on the shuffle that distributes the atomic's result - the counters saw one
+// request every 2-3 cycles); here the warps add up in shared memory and one thread per queue asks for the block's slots.
+// Every thread of the block must call (two barriers).  s_cnt must be zero on entry and is zero again on return.
+enum { APPEND_TREEQ = MQ_CLASSES, APPEND_SLOTS = MQ_CLASSES + 1, APPEND_NONE = APPEND_SLOTS };
+// slot: a material class (append to its queue of set 0), APPEND_TREEQ (the mesh walk's ray queue) or APPEND_NONE
+__device__ __forceinline__ uint32_t block_append_slots(const WfParams& p, int slot, uint32_t* s_cnt, uint32_t* s_base) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned grp = __match_any_sync(0xffffffffu, slot);
+    const int leader = __ffs(grp) - 1;
+    uint32_t woff = 0;
+    if (slot < APPEND_SLOTS && (int)lane == leader) woff = atomicAdd(s_cnt + slot, (uint32_t)__popc(grp));
+    __syncthreads();
+    if (threadIdx.x < APPEND_SLOTS) {
+        const uint32_t c = s_cnt[threadIdx.x];
+        s_base[threadIdx.x] = c ? atomicAdd(threadIdx.x == APPEND_TREEQ ? p.cnt + CNT_TREEQ : p.cnt + CNT_MQ + threadIdx.x, c) : 0u;
+        s_cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    if (slot >= APPEND_SLOTS) return 0;
+    woff = __shfl_sync(grp, woff, leader);
+    return s_base[slot] + woff + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+}
 // ---------------------------------------------------------------------------- TMA bulk copy helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -398,18 +422,10 @@ __global__ void __launch_bounds__(THREADS, 1) wf_extend_list() {
 enum { BVH1_NONE = 0xffff, BVH1_DROP = 0xfffe };   // obj field of a record: no hit / path ends without a contribution
 // record: x = t bits, y = obj | face << 16 | post << 24 (post: the list hit comes after the Bvh in list order), z = prim_ref
 
-// appends ray i + its hit record to the queue of the hit's material kind (all 32 lanes call; kind 7 = nothing to append)
-__device__ __forceinline__ void bvh1_append(const WfParams& p, int cur, uint32_t i, int kind, const f4& hv) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const unsigned grp = __match_any_sync(0xffffffffu, kind);
-    if (kind < MQ_CLASSES) {   // lanes with the same kind share one atomic
-        const int leader = __ffs(grp) - 1;
-        uint32_t base = 0;
-        if ((int)lane == leader) base = atomicAdd(p.cnt + CNT_MQ + kind, (uint32_t)__popc(grp));
-        base = __shfl_sync(grp, base, leader);
-        const size_t pos = mq_slot(p, 0, kind, base + (uint32_t)__popc(grp & ((1u << lane) - 1u)));
-        p.mq_o[pos] = p.ray_o[cur][i]; p.mq_d[pos] = p.ray_d[cur][i]; p.mq_thr[pos] = p.thr[cur][i]; p.mq_hit[pos] = hv;
-    }
+// writes ray i + its hit record as entry j of the queue of material class `kind`
+__device__ __forceinline__ void bvh1_write_entry(const WfParams& p, int cur, uint32_t i, int kind, uint32_t j, const f4& hv) {
+    const size_t pos = mq_slot(p, 0, kind, j);
+    p.mq_o[pos] = p.ray_o[cur][i]; p.mq_d[pos] = p.ray_d[cur][i]; p.mq_thr[pos] = p.thr[cur][i]; p.mq_hit[pos] = hv;
 }
 // a ray's final record -> background (ray.rs:60) or the material kind + hit record to append
 __device__ __forceinline__ int bvh1_resolve(const WfParams& p, const SceneView& sv, int cur, uint32_t i, const i4& rec, f4& hv) {
@@ -441,12 +457,13 @@ __global__ void __launch_bounds__(256) wf_bvh1_list() {
     const SceneView& sv = p.sv;
     const int cur = (int)p.cnt[CNT_CUR];
     const uint32_t n = p.cnt[cur];
-    const uint32_t n_round = (n + 31u) & ~31u;
-    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const int bo = p.bvh1_index;
     uint32_t prims = 0;
     __shared__ f4 s_rect[2 * SHIM_BVH1_LIST_RECTS];
     __shared__ int s_obj[SHIM_BVH1_LIST_RECTS], s_ref[SHIM_BVH1_LIST_RECTS];
+    __shared__ uint32_t s_cnt[APPEND_SLOTS], s_base[APPEND_SLOTS];
+    if (threadIdx.x < APPEND_SLOTS) s_cnt[threadIdx.x] = 0;
+    if (!RECTS) __syncthreads();
     if (RECTS) {
         if ((int)threadIdx.x < sv.n_objects && (int)threadIdx.x != bo) {
             const int m = (int)threadIdx.x - ((int)threadIdx.x > bo ? 1 : 0);   // list order is kept
@@ -457,9 +474,10 @@ __global__ void __launch_bounds__(256) wf_bvh1_list() {
         }
         __syncthreads();
     }
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // block-uniform trip count (barriers inside)
+        const uint32_t i = base + threadIdx.x;
         bool need = false;
-        int kind = 7;
+        int kind = APPEND_NONE;
         f4 hv;
         if (i < n) {
             f4 o = p.ray_o[cur][i], d = p.ray_d[cur][i];
@@ -500,14 +518,9 @@ __global__ void __launch_bounds__(256) wf_bvh1_list() {
             if (need) p.bvh1_hit[i] = rec;                      // the walk may replace it, wf_bvh1_finish writes it out
             else kind = bvh1_resolve(p, sv, cur, i, rec, hv);   // final already
         }
-        const unsigned nmask = __ballot_sync(0xffffffffu, need);
-        if (nmask) {
-            uint32_t at = 0;
-            if (lane == (uint32_t)(__ffs(nmask) - 1)) at = atomicAdd(p.cnt + CNT_TREEQ, (uint32_t)__popc(nmask));
-            at = __shfl_sync(0xffffffffu, at, __ffs(nmask) - 1);
-            if (need) p.bvh1_queue[at + (uint32_t)__popc(nmask & lt_mask)] = i;
-        }
-        bvh1_append(p, cur, i, kind, hv);
+        const uint32_t at = block_append_slots(p, need ? (int)APPEND_TREEQ : kind, s_cnt, s_base);
+        if (need) p.bvh1_queue[at] = i;
+        else if (kind < MQ_CLASSES) bvh1_write_entry(p, cur, i, kind, at, hv);
     }
     if (COUNT) atomicAdd(cnt64(p.cnt, C64_PRIMS), (unsigned long long)prims);
 }
@@ -664,16 +677,21 @@ __global__ void __launch_bounds__(256) wf_bvh1_finish() {
     const SceneView& sv = p.sv;
     const int cur = (int)p.cnt[CNT_CUR];
     const uint32_t n = p.cnt[CNT_TREEQ];
-    const uint32_t n_round = (n + 31u) & ~31u;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
-        int kind = 7;
+    __shared__ uint32_t s_cnt[APPEND_SLOTS], s_base[APPEND_SLOTS];
+    if (threadIdx.x < APPEND_SLOTS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t j = base + threadIdx.x;
+        int kind = APPEND_NONE;
         f4 hv;
         uint32_t i = 0;
         if (j < n) {
             i = p.bvh1_queue[j];
             kind = bvh1_resolve(p, sv, cur, i, p.bvh1_hit[i], hv);
+            if (kind >= MQ_CLASSES) kind = APPEND_NONE;
         }
-        bvh1_append(p, cur, i, kind, hv);
+        const uint32_t at = block_append_slots(p, kind, s_cnt, s_base);
+        if (kind < MQ_CLASSES) bvh1_write_entry(p, cur, i, kind, at, hv);
     }
 }
 
@@ -720,7 +738,7 @@ __device__ __forceinline__ void shade_chunk(const WfParams& p, int cur, uint32_t
         shade_one<KIND>(p, p.sv, r, h, f2i(hv.w), mk3(t.x, t.y, t.z), (int)(bs & 255u), pixel, bs >> 8, so);
     }
     if (KIND != MAT_DIFFUSE_LIGHT) {
-        uint32_t pos = warp_append(p.cnt + nxt, so.cont);
+        uint32_t pos = warp_append(p.cnt + nxt, so.cont);   // (a block-wide append measured 1 % slower here: one counter, long chunks)
         if (so.cont) {
             f4 o; o.x = so.ray.o.x; o.y = so.ray.o.y; o.z = so.ray.o.z; o.w = so.ray.time;
             f4 d; d.x = so.ray.d.x; d.y = so.ray.d.y; d.z = so.ray.d.z; d.w = i2f((int)(bs + 1u));
@@ -734,7 +752,7 @@ __device__ __forceinline__ void shade_chunk(const WfParams& p, int cur, uint32_t
 
 // One launch for all material queues: the queues are cut into 256-ray chunks, chunks are dealt
 // round-robin to the persistent blocks, and each chunk runs the code specialised for its material.
-__global__ void __launch_bounds__(256) wf_shade() {
+__global__ void __launch_bounds__(256) wf_shade() {   // 72 registers, 3 blocks per SM (forcing 4 or 5: 1-7 % slower)
     const WfParams& p = g_p;
     const int cur = (int)p.cnt[CNT_CUR];
     uint32_t n[MQ_CLASSES], first[MQ_CLASSES + 1];
