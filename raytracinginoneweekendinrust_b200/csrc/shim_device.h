@@ -709,10 +709,23 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
         c.r = object_ray(ob, ray);
         if (HASBVH && ob.kind == OBJ_BVH) make_ctx(c, c.r);  // reciprocals are only needed for box tests
         float t; uint32_t prim; int face;
-        if (ob.flags & OBJ_MEDIUM) {
-            float t1, t2;
-            if (!shape_hit<COUNT, HRPP, HASBVH, QN>(sv, ob, c, -SHIM_INF, SHIM_INF, t1, prim, face, cnt)) continue;
-            if (!shape_hit<COUNT, HRPP, HASBVH, QN>(sv, ob, c, t1 + 0.0001f, SHIM_INF, t2, prim, face, cnt)) continue;
+        // One copy of the shape code serves all three calls (a medium asks its boundary twice, hittable.rs:190-199):
+        // with shape_hit inlined three times the generic kernel was 7 100 instructions and 18 % of its stall samples
+        // were instruction fetches.
+        const bool medium = (ob.flags & OBJ_MEDIUM) != 0;
+        float lo = medium ? -SHIM_INF : t_min, hi = medium ? SHIM_INF : closest, t1 = 0.0f;
+        bool found = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int pass = 0; pass < 2; ++pass) {
+            found = shape_hit<COUNT, HRPP, HASBVH, QN>(sv, ob, c, lo, hi, t, prim, face, cnt);
+            if (!found || !medium || pass == 1) break;
+            t1 = t; lo = t1 + 0.0001f;
+        }
+        if (!found) continue;
+        if (medium) {
+            float t2 = t;
             if (t1 < t_min) t1 = t_min;
             if (t2 > closest) t2 = closest;
             if (t1 >= t2) continue;
@@ -724,7 +737,7 @@ SHIM_HD Hit closest_hit(const SceneView& sv, const Ray& ray, float t_min, float 
             t = t1 + hit_distance / ray_length;
             closest = t;
             h.t = t; h.obj = oi; h.prim = 0; h.face = 0;
-        } else if (shape_hit<COUNT, HRPP, HASBVH, QN>(sv, ob, c, t_min, closest, t, prim, face, cnt)) {
+        } else {
             closest = t;
             h.t = t; h.obj = oi; h.prim = prim; h.face = face;
         }
