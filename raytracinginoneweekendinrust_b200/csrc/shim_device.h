@@ -452,7 +452,7 @@ SHIM_HD void slab_pair_q(const uint32_t* w, const RayCtx& c, float t_min, float 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float inv = k == 0 ? c.inv_d.x : (k == 1 ? c.inv_d.y : c.inv_d.z), oinv = k == 0 ? c.o_inv.x : (k == 1 ? c.o_inv.y : c.o_inv.z);
-        const float a = i2f((int)((w[k] & 0xffu) << 23)) * inv;
+        const float a = i2f((int)(w[k] << 23)) * inv;   // bits 0-7 = exponent byte, bit 8 = 0 (sign)
         const float b = slab_plane(i2f((int)w[k]), inv, oinv) - a;
         const uint32_t q = rotl32(w[3 + k], c.qrot[k]);   // bytes {near_l, near_r, far_l, far_r}
         nl[k] = slab_plane(i2f((int)byte_perm32(q, 0x3F800000u, 0x7604u)), a, b);

@@ -631,10 +631,10 @@ bool qgrid(float lo, float hi, uint32_t& o_bits, double& origin, double& step) {
         const double x = (double)lo - S;   // one step below the lowest plane
         float xf = (float)x;
         if ((double)xf > x) xf = std::nextafterf(xf, -INFINITY);
-        uint32_t b = (f32_bits(xf) & ~0xffu) | (uint32_t)E;
-        if ((double)bits_f32(b) > x) {      // the exponent byte moved the value up: one 256-ulp step towards -inf
-            if (b & 0x80000000u) b += 256u;
-            else if (b >= 512u) b -= 256u;
+        uint32_t b = (f32_bits(xf) & ~0x1ffu) | (uint32_t)E;   // bit 8 stays clear: (word << 23) is then the step's float
+        if ((double)bits_f32(b) > x) {      // the exponent byte moved the value up: one 512-ulp step towards -inf
+            if (b & 0x80000000u) b += 512u;
+            else if (b >= 1024u) b -= 512u;
             else b = 0x80000000u | (uint32_t)E;   // below the smallest positive grid value: a negative denormal
         }
         const double o = (double)bits_f32(b);

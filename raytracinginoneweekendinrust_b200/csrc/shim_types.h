@@ -85,8 +85,9 @@ struct alignas(16) SNode {
 // hit rates, a 4.9 k-triangle tree fits shared memory whole).  Per axis a grid origin o and a power-of-two step S; a
 // child plane is o + q * S with an 8-bit q, rounded OUTWARDS by at least one step, so the decoded boxes contain the
 // exact ones (a walk over larger boxes visits more candidates and returns the same hit, see bvh_closest).
-//   o[k]   f32 bits of the origin; its low mantissa byte doubles as the IEEE exponent byte of 2^15 * S (the origin is
-//          the float those 32 bits spell, exponent byte included: the builder quantises against exactly that value)
+//   o[k]   f32 bits of the origin; its low mantissa byte doubles as the IEEE exponent byte of 2^15 * S and bit 8 is
+//          clear, so (o[k] << 23) is the float 2^15 * S (the origin is the float those 32 bits spell, exponent byte
+//          included: the builder quantises against exactly that value)
 //   q[k]   bytes {l.min, r.min, l.max, r.max}; an empty child slot is {.., 255, .., 0}: never hit
 //   left/right   >= 0 index into the QNode array (breadth-first order, root = 0: the first K nodes are the top of the
 //          tree), < 0 ~prim_ref, CHILD_NONE
