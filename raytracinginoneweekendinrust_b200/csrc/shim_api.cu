@@ -294,8 +294,10 @@ SHIM_API int shim_commit(shim_scene* s) {
         const int idx = single_bvh_object(s->flat);
         if (!media && bvh1_triangles_only(s->flat, idx)) s->flat.build_quantized_nodes(idx);
     }
+    lap("quantised nodes");
     const FlatScene& f = s->flat;
     SceneBlob& b = st->blob;
+    b.bytes.reserve((size_t)f.bytes() + 64 * 256);   // one allocation (growing a 40 MB vector array by array was a third of a large commit)
     auto put = [&](const void* src, size_t bytes) -> size_t {
         size_t off = (b.bytes.size() + 255) & ~(size_t)255;
         b.bytes.resize(off + (bytes ? bytes : 16));

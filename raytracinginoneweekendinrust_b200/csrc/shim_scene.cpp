@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
 #include <functional>
+#include <thread>
 
 namespace shim {
 
@@ -617,29 +619,39 @@ void FlatScene::build_signed_nodes() {
 namespace {
 uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 float bits_f32(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+double pow2(int s) { const uint64_t u = (uint64_t)(s + 1023) << 52; double d; memcpy(&d, &u, 8); return d; }   // -1022 <= s <= 1023
+double floor_pos(double v) { return (double)(int64_t)v; }                                                    // 0 <= v < 2^62
+double ceil_pos(double v) { const double f = (double)(int64_t)v; return f < v ? f + 1.0 : f; }
 // grid of one axis for planes in [lo, hi]: origin bits (low byte = exponent byte of 2^15 * step) and the step
 bool qgrid(float lo, float hi, uint32_t& o_bits, double& origin, double& step) {
     if (!std::isfinite(lo) || !std::isfinite(hi) || std::fabs(lo) > 4096.0f || std::fabs(hi) > 4096.0f || hi < lo) return false;
     const double ext = (double)hi - (double)lo;
-    int s = ext > 0.0 ? (int)std::ceil(std::log2(ext / 252.0)) : std::ilogb(std::fmax(std::fabs((double)lo), 1e-30)) - 20;
+    int s;
+    if (ext > 0.0) {   // smallest s with 2^s >= ext / 252
+        int e;
+        const double m = std::frexp(ext / 252.0, &e);   // = m * 2^e, m in [0.5, 1)
+        s = m == 0.5 ? e - 1 : e;
+    } else {
+        s = std::ilogb(std::fmax(std::fabs((double)lo), 1e-30)) - 20;
+    }
     if (s < -126) s = -126;
     for (;; ++s) {
         const int E = s + 15 + 127;
         if (E < 1) continue;
         if (E > 254) return false;
-        const double S = std::ldexp(1.0, s);
+        const double S = pow2(s);
         const double x = (double)lo - S;   // one step below the lowest plane
-        float xf = (float)x;
-        if ((double)xf > x) xf = std::nextafterf(xf, -INFINITY);
-        uint32_t b = (f32_bits(xf) & ~0x1ffu) | (uint32_t)E;   // bit 8 stays clear: (word << 23) is then the step's float
-        if ((double)bits_f32(b) > x) {      // the exponent byte moved the value up: one 512-ulp step towards -inf
+        // (float)x may round up by half an ulp, clearing the low bits moves a negative value up by < 512 ulps and the
+        // exponent byte a positive one by < 256: one 512-ulp step down covers all of it (checked below)
+        uint32_t b = (f32_bits((float)x) & ~0x1ffu) | (uint32_t)E;   // bit 8 stays clear: (word << 23) is then the step's float
+        if ((double)bits_f32(b) > x) {      // one 512-ulp step towards -inf
             if (b & 0x80000000u) b += 512u;
             else if (b >= 1024u) b -= 512u;
             else b = 0x80000000u | (uint32_t)E;   // below the smallest positive grid value: a negative denormal
         }
         const double o = (double)bits_f32(b);
         if (!(o <= x) || !std::isfinite(o)) continue;
-        if (std::ceil(((double)hi - o) / S) + 1.0 > 255.0) continue;
+        if (ceil_pos(((double)hi - o) * pow2(-s)) + 1.0 > 255.0) continue;
         o_bits = b; origin = o; step = S;
         return true;
     }
@@ -650,14 +662,22 @@ bool FlatScene::build_quantized_nodes(int oi) {
     q_object = -1;
     if (oi < 0 || oi >= (int)objects.size() || objects[oi].kind != OBJ_BVH) return false;
     std::vector<int> order{objects[oi].ref};   // QNode index -> DevNode index, breadth-first
-    std::unordered_map<int, int> qindex{{objects[oi].ref, 0}};
+    order.reserve((size_t)objects[oi].n_nodes);
+    std::vector<int> qindex(nodes.size(), -1);
+    qindex[objects[oi].ref] = 0;
     for (size_t h = 0; h < order.size(); ++h) {
+        if (h + 16 < order.size()) __builtin_prefetch(&nodes[order[h + 16]].d);   // breadth-first order is random in memory
         const DevNode& n = nodes[order[h]];
         for (int c : {n.d.x, n.d.y})
             if (c >= 0) { qindex[c] = (int)order.size(); order.push_back(c); }
     }
     std::vector<QNode> out(order.size());
-    for (size_t i = 0; i < order.size(); ++i) {
+    // the nodes are independent: large trees (the commit of a 267 k-triangle mesh is inside the end-to-end time) are
+    // quantised by a few threads
+    std::atomic<bool> ok{true};
+    auto quantise = [&](size_t begin, size_t end) {
+      for (size_t i = begin; i < end; ++i) {
+        if (i + 16 < end) __builtin_prefetch(&nodes[order[i + 16]]);
         const DevNode& n = nodes[order[i]];
         const bool has_r = n.d.y != CHILD_NONE;
         const float lmn[3] = {n.a.x, n.a.y, n.a.z}, lmx[3] = {n.a.w, n.b.x, n.b.y};
@@ -666,15 +686,31 @@ bool FlatScene::build_quantized_nodes(int oi) {
         for (int k = 0; k < 3; ++k) {
             const float lo = has_r ? std::fmin(lmn[k], rmn[k]) : lmn[k], hi = has_r ? std::fmax(lmx[k], rmx[k]) : lmx[k];
             double origin, S;
-            if (!qgrid(lo, hi, q.o[k], origin, S)) return false;
-            auto down = [&](float v) { return (uint32_t)(std::floor(((double)v - origin) / S) - 1.0); };
-            auto up = [&](float v) { return (uint32_t)(std::ceil(((double)v - origin) / S) + 1.0); };
-            if (!(lmn[k] <= lmx[k]) || (has_r && !(rmn[k] <= rmx[k]))) return false;
+            if (!qgrid(lo, hi, q.o[k], origin, S)) { ok = false; return; }
+            const double inv_S = 1.0 / S;   // a power of two: exact
+            auto down = [&](float v) { return (uint32_t)(floor_pos(((double)v - origin) * inv_S) - 1.0); };   // v - origin >= S
+            auto up = [&](float v) { return (uint32_t)(ceil_pos(((double)v - origin) * inv_S) + 1.0); };
+            if (!(lmn[k] <= lmx[k]) || (has_r && !(rmn[k] <= rmx[k]))) { ok = false; return; }
             q.q[k] = down(lmn[k]) | (has_r ? down(rmn[k]) : 255u) << 8 | up(lmx[k]) << 16 | (has_r ? up(rmx[k]) : 0u) << 24;
         }
         q.left = n.d.x >= 0 ? qindex[n.d.x] : n.d.x;
         q.right = n.d.y >= 0 ? qindex[n.d.y] : n.d.y;
+      }
+    };
+    unsigned n_threads = order.size() >= 32768 ? std::thread::hardware_concurrency() : 1;
+    if (n_threads > 8) n_threads = 8;
+    if (n_threads <= 1) {
+        quantise(0, order.size());
+    } else {
+        std::vector<std::thread> pool;
+        const size_t per = (order.size() + n_threads - 1) / n_threads;
+        for (unsigned t = 0; t < n_threads; ++t) {
+            const size_t b = t * per, e = b + per < order.size() ? b + per : order.size();
+            if (b < e) pool.emplace_back(quantise, b, e);
+        }
+        for (std::thread& t : pool) t.join();
     }
+    if (!ok) return false;
     qnodes.swap(out);
     q_object = oi;
     return true;
