@@ -366,7 +366,7 @@ def measure_extra(label, key, kw, with_cpu, args, api, capi, scenes, torch, dev,
     # end to end: commit + render into a page-locked host framebuffer
     hfb = api.HostFramebuffer(H, W)
     e2e = []
-    for k in range(3):
+    for k in range(4):
         s2 = api.Scene()
         scenes.SCENES[cfg.scene](s2, seed=1, **kwargs)       # host-side recording (untimed, like Bvh::new in the reference)
         torch.cuda.synchronize(dev)
@@ -374,11 +374,15 @@ def measure_extra(label, key, kw, with_cpu, args, api, capi, scenes, torch, dev,
         s2.commit()
         _, st2 = s2.render(cfg.camera, api.make_params(W, H, spp, cfg.max_depth, background=info.background, seed=0, flags=base), out=hfb.array)
         dt = time.perf_counter() - t0
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"{label} e2e step {k}: {1e3 * dt:.2f} ms (device {st2.device_ms:.2f} ms, {st2.iterations} iterations, pool {st2.pool_paths})", file=sys.stderr)
         if k > 0:
             e2e.append((dt, st2.rays))
         s2.close()
     hfb.close()
-    out["e2e"] = {"value": sum(r for _, r in e2e) / sum(t for t, _ in e2e) / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * sum(t for t, _ in e2e) / len(e2e),
+    e2e.sort()
+    dt_med, rays_med = e2e[len(e2e) // 2]   # median of the three calls after the warm-up one (a host hiccup of tens of ms is common next to the CPU legs)
+    out["e2e"] = {"value": rays_med / dt_med / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * dt_med, "calls": len(e2e), "statistic": "median",
                   "h2d_bytes_per_step": scene.device_bytes(), "d2h_bytes_per_step": W * H * 12}
     scene.close()
     del fb
