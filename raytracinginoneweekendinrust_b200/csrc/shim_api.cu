@@ -361,7 +361,7 @@ static int wf_init(Wavefront& w, int device) {
     CU(opt_in_smem(wf_extend<true, false, false, true>, dyn));  CU(opt_in_smem(wf_extend<true, false, true, true>, dyn));
     CU(opt_in_smem(wf_bvh1_walk<true, false>, dyn));  CU(opt_in_smem(wf_bvh1_walk<true, true>, dyn));
     CU(opt_in_smem(wf_bvh1_walk<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI>, dyn));
-    CU(opt_in_smem(wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI, true>, dyn));
+    CU(opt_in_smem(wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI, 1>, dyn));
     CU(opt_in_smem(wf_extend_list<false, SHIM_LIST_THREADS>, dyn)); CU(opt_in_smem(wf_extend_list<true, SHIM_LIST_THREADS>, dyn));
     CU(opt_in_smem(wf_extend_list<false, SHIM_LIST_THREADS, true>, dyn)); CU(opt_in_smem(wf_extend_list<true, SHIM_LIST_THREADS, true>, dyn));
     CU(opt_in_smem(wf_extend_solo<false, SHIM_SOLO_SPHERE_THREADS, PT_SPHERE, false>, dyn));
@@ -438,7 +438,7 @@ static void choose_variant(const shim_scene* s, const shim::DeviceState* st, con
         k.bvh1_list_rects = plain_rects ? 1 : 0;
     }
     if (k.bvh1_index >= 0 && !sw.no_bvh1_tri && bvh1_triangles_only(f, k.bvh1_index)) k.bvh1_tri_threads = SHIM_BVH1_TRI_THREADS;
-    // quantised nodes (built at commit for exactly these worlds): the top of the tree in shared memory, as much as fits
+    // quantised nodes (built at commit for exactly these worlds): staged in shared memory when the whole tree fits
     k.bvh1_q = 0; k.bvh1_q_smem = 0;
     if (k.bvh1_tri_threads && !k.count_nodes && !f.qnodes.empty() && f.q_object == k.bvh1_index && !sw.no_qnodes) {
         k.bvh1_q = 1;
@@ -447,9 +447,8 @@ static void choose_variant(const shim_scene* s, const shim::DeviceState* st, con
         if (cap > w.max_smem - 2048) cap = w.max_smem - 2048;
         const size_t fit = cap > 0 ? (size_t)cap / sizeof(QNode) : 0;
         // all of the tree or none of it: a staged top of a larger tree was measured slower than leaving the whole
-        // shared-memory carve-out to L1 (igea, 267 k triangles: 92.0 ms with the top 160 KB staged, 90.0 ms without);
-        // SHIM_Q_SMEM_KB set explicitly stages the top that fits
-        k.bvh1_q_smem = f.qnodes.size() <= fit ? (uint32_t)f.qnodes.size() : (sw.q_smem_kb >= 0 ? (uint32_t)fit : 0u);
+        // shared-memory carve-out to L1 (igea, 267 k triangles: 92.0 ms with the top 160 KB staged, 90.0 ms without)
+        k.bvh1_q_smem = f.qnodes.size() <= fit ? (uint32_t)f.qnodes.size() : 0u;
     }
     k.list_threads = 0;
     if (use_smem && !k.count_nodes && !k.use_hrpp && f.nodes.empty() && !k.solo && !sw.no_list) {
@@ -501,7 +500,8 @@ static void launch_extend(const Wavefront& w, const WfParams& k, bool use_smem, 
         else wf_bvh1_list<false><<<w.grid_stream, 256, 0, st>>>();
         const int wgrid = S ? w.sm_count : w.grid_bvh1_walk;
         if (k.bvh1_q) {   // triangle-only tree on quantised nodes, one block per SM owns the shared-memory top of the tree
-            wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI, true><<<w.sm_count, SHIM_BVH1_TRI_THREADS, k.bvh1_q_smem * (uint32_t)sizeof(QNode), st>>>();
+            if (k.bvh1_q_smem) wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI, 1><<<w.sm_count, SHIM_BVH1_TRI_THREADS, k.bvh1_q_smem * (uint32_t)sizeof(QNode), st>>>();
+            else wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI, 2><<<w.sm_count, SHIM_BVH1_TRI_THREADS, 0, st>>>();
         } else if (k.bvh1_tri_threads && !C) {   // triangle-only tree: no primitive dispatch, more warps
             if (S) wf_bvh1_walk<true, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<wgrid, SHIM_BVH1_TRI_THREADS, smem, st>>>();
             else wf_bvh1_walk<false, false, SHIM_BVH1_TRI_THREADS, PT_TRI><<<wgrid, SHIM_BVH1_TRI_THREADS, 0, st>>>();

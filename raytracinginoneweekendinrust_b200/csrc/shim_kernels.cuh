@@ -357,7 +357,7 @@ __device__ __forceinline__ SceneView stage_scene(const WfParams& p, unsigned cha
 #define SHIM_SOLO_ANY_THREADS 768      // one plain Bvh of mixed primitives: 80 registers
 #define SHIM_LIST_THREADS 1024         // worlds without a Bvh: 64 registers
 #ifndef SHIM_BVH1_TRI_THREADS
-#define SHIM_BVH1_TRI_THREADS 896      // one triangle-only Bvh among rects
+#define SHIM_BVH1_TRI_THREADS 1024     // one triangle-only Bvh among rects (56-63 registers)
 #endif
 template <bool SMEM, bool COUNT, bool MEDIA, bool HRPP>
 __global__ void __launch_bounds__(SHIM_EXTEND_THREADS, 1) wf_extend() {
@@ -528,10 +528,10 @@ __global__ void __launch_bounds__(256) wf_bvh1_list() {
 #ifndef SHIM_BVH1_PRIM_BATCH
 #define SHIM_BVH1_PRIM_BATCH 8
 #endif
-// QN: the tree is walked on its quantised 32-byte nodes (QNode, breadth-first order): the first p.bvh1_q_smem of them -
-// the top of the tree, or all of it - are staged in shared memory by bulk copies, the rest is fetched with one 32-byte
+// QN: the tree is walked on its quantised 32-byte nodes (QNode, breadth-first order).  1: all of them are staged in
+// shared memory by bulk copies (p.bvh1_q_smem = their number); 2: they are fetched from global memory with one 32-byte
 // load per node.  (SMEM and QN exclude each other.)
-template <bool SMEM, bool COUNT, int THREADS = SHIM_EXTEND_THREADS, int ONLY = -1, bool QN = false>
+template <bool SMEM, bool COUNT, int THREADS = SHIM_EXTEND_THREADS, int ONLY = -1, int QN = 0>
 __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
     const WfParams& p = g_p;
     const int cur_q = (int)p.cnt[CNT_CUR];
@@ -540,8 +540,8 @@ __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const SceneView sv = SMEM ? stage_scene(p, smem, &bar) : p.sv;
-    const uint32_t q_smem = p.bvh1_q_smem;   // 0 unless QN
-    if (QN && q_smem) {
+    if (QN == 1) {
+        const uint32_t q_smem = p.bvh1_q_smem;
         if (threadIdx.x == 0) mbar_init(&bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -597,10 +597,11 @@ __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
         for (;;) {
             // ---- node rounds
             for (;;) {
-                const bool at_node = active && cur >= 0 && cur != SHIM_STACK_END;
+                // (an idle lane has cur == SHIM_STACK_END: cur alone tells the three states apart)
+                const bool at_node = (uint32_t)cur < (uint32_t)SHIM_STACK_END;
                 const unsigned nm = __ballot_sync(0xffffffffu, at_node);
                 if (nm == 0u) break;
-                const unsigned pm = __ballot_sync(0xffffffffu, active && cur < 0);
+                const unsigned pm = __ballot_sync(0xffffffffu, cur < 0);
                 if (__popc(pm) >= SHIM_BVH1_PRIM_BATCH) break;
                 if (at_node) {
                     i4 ch;
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
                     if (COUNT) nodes++;
                     if (QN) {
                         uint32_t w[8];
-                        if ((uint32_t)cur < q_smem) {
+                        if (QN == 1) {
                             const uint32_t a = q_base + (uint32_t)cur * (uint32_t)sizeof(QNode);
                             asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
                             asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+16];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(a));
