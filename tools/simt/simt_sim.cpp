@@ -11,6 +11,8 @@
 // Costs are issue slots per warp instruction group, taken from the SASS of the round-1 kernel.
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "../../raytracinginoneweekendinrust_b200/csrc/shim_device.h"
@@ -178,6 +180,22 @@ extern "C" __attribute__((visibility("default"))) int simt_sim(shim_scene* s, co
                 double* o = out + 4 * (pi * max_b + iter);
                 o[0] += (double)rays.size(); o[1] += ws.slots; o[2] += ws.useful; o[3] += ws.bound_max;
             }
+        }
+        // experiment (SIMT_SORT_WINDOW=N): the entries of each material queue sorted by the Morton key of their hit point
+        // inside windows of N consecutive entries (what a block could do in shared memory before it appends)
+        if (const char* sw = getenv("SIMT_SORT_WINDOW")) {
+            const size_t win = (size_t)atol(sw);
+            auto key = [](const Entry& e) {
+                const f3 pt = e.r.o + e.h.t * e.r.d;
+                auto q10 = [](float v) { float u = (v + 16.0f) / 32.0f; u = u < 0 ? 0 : (u > 0.999f ? 0.999f : u); return (uint32_t)(u * 1024.0f); };
+                auto spread = [](uint32_t x) { x &= 1023u; x = (x | (x << 16)) & 0x30000ffu; x = (x | (x << 8)) & 0x300f00fu; x = (x | (x << 4)) & 0x30c30c3u; x = (x | (x << 2)) & 0x9249249u; return x; };
+                return spread(q10(pt.x)) | (spread(q10(pt.y * 8.0f - 12.0f)) << 1) | (spread(q10(pt.z)) << 2);
+            };
+            for (int seg = 1; seg <= MAT_KINDS; ++seg)
+                for (size_t b0 = 0; win && b0 < nq[seg].size(); b0 += win) {
+                    auto first = nq[seg].begin() + b0, last = nq[seg].begin() + std::min(nq[seg].size(), b0 + win);
+                    std::stable_sort(first, last, [&](const Entry& a, const Entry& b) { return key(a) < key(b); });
+                }
         }
         for (int seg = 0; seg <= MAT_KINDS; ++seg) q[seg].swap(nq[seg]);
         q[0].clear();
