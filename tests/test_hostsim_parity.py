@@ -147,3 +147,46 @@ def test_quantised_nodes_return_the_same_hits(name, kw):
     np.testing.assert_array_equal(p_ref, p1)
     assert nq > 0 and c1[1] >= c0[1] * 0.999          # larger boxes: never fewer node visits (up to the near/far order)
     assert c1[1] <= c0[1] * 1.25, (c0, c1)             # ... and not many more
+
+
+@pytest.mark.parametrize("case", ["flat", "tiny", "far", "negative", "sliver"])
+def test_quantised_nodes_on_degenerate_meshes(case):
+    """Grid edge cases of the QNode builder (shim_scene.cpp: qgrid): a mesh inside one axis-parallel plane (zero extent on
+    an axis), triangles 1e-4 apart near coordinate 500 (the step approaches an ulp of the origin), a mesh near the
+    representable limit of 4096, negative coordinates, long thin triangles.  The quantised walk must still return the
+    exact walk's hits, bit for bit, for rays aimed at the mesh, grazing it and parallel to its plane."""
+    rs = np.random.RandomState(7)
+    n = 600
+    a = rs.uniform(0.0, 1.0, (n, 3, 3)).astype(np.float32)
+    if case == "flat":
+        tris = a * np.array([120.0, 0.0, 120.0], np.float32) + np.array([0.0, 40.0, 0.0], np.float32)
+    elif case == "tiny":
+        tris = np.float32(500.0) + a * np.float32(1e-3)
+    elif case == "far":
+        tris = np.float32(3900.0) + a * np.float32(150.0)
+    elif case == "negative":
+        tris = a * np.float32(200.0) - np.float32(650.0)
+    else:
+        base = rs.uniform(0.0, 100.0, (n, 1, 3)).astype(np.float32)
+        tris = base + a * np.array([300.0, 1e-3, 1e-3], np.float32)
+    tris = np.ascontiguousarray(tris, np.float32)
+    o, h = support.OracleScene(), support.HostSimScene()
+    for s in (o, h):
+        scenes._mesh_in_cornell(s, case, tris, (0.0, 0.0, 0.0), 1)
+        s.commit()
+    centre = tris.reshape(-1, 3).mean(axis=0)
+    size = float(np.abs(tris.reshape(-1, 3) - centre).max()) + 1e-3
+    k = 6000
+    org = (centre + rs.normal(size=(k, 3)) * size * 3.0).astype(np.float32)
+    tgt = tris.reshape(-1, 3)[rs.randint(0, n * 3, k)] + rs.normal(size=(k, 3)).astype(np.float32) * np.float32(size * 0.02)
+    d = (tgt - org).astype(np.float32)
+    d[: k // 6, 1] = 0.0                                  # parallel to the y planes (the flat mesh's plane)
+    d[k // 6: k // 3, rs.randint(0, 3)] = -0.0
+    rays = np.concatenate([org, d, np.zeros((k, 1), np.float32)], axis=1).astype(np.float32)
+    p0, t0 = h.trace_closest(rays)
+    p1, t1, _, nq = h.trace_closest_q(rays)
+    np.testing.assert_array_equal(p0, p1)
+    np.testing.assert_array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    p_ref, t_ref = o.trace_closest(rays, seed=0)
+    np.testing.assert_array_equal(p_ref, p1)
+    assert (p1 >= 0).sum() > k // 20                      # the rays do reach the mesh
