@@ -528,6 +528,9 @@ __global__ void __launch_bounds__(256) wf_bvh1_list() {
 #ifndef SHIM_BVH1_PRIM_BATCH
 #define SHIM_BVH1_PRIM_BATCH 8
 #endif
+#ifndef SHIM_BVH1_STEPS_PER_VOTE
+#define SHIM_BVH1_STEPS_PER_VOTE 2
+#endif
 // QN: the tree is walked on its quantised 32-byte nodes (QNode, breadth-first order).  1: all of them are staged in
 // shared memory by bulk copies (p.bvh1_q_smem = their number); 2: they are fetched from global memory with one 32-byte
 // load per node.  (SMEM and QN exclude each other.)
@@ -595,7 +598,44 @@ __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
         }
         if (!__any_sync(0xffffffffu, active)) continue;   // (`more` is false by now: the loop ends)
         for (;;) {
-            // ---- node rounds
+            // ---- node rounds.  The votes that steer a round are a sixth of its instructions, so the quantised walk takes
+            // SHIM_BVH1_STEPS_PER_VOTE node steps per vote (a lane that reaches a primitive early waits for the batch anyway).
+            auto node_step = [&]() {
+                i4 ch;
+                float tl, tr;
+                bool hl, hr;
+                if (COUNT) nodes++;
+                if (QN) {
+                    uint32_t w[8];
+                    if (QN == 1) {
+                        const uint32_t a = q_base + (uint32_t)cur * (uint32_t)sizeof(QNode);
+                        asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
+                        asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+16];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(a));
+                    } else {
+                        asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(sv.qnodes + cur));
+                    }
+                    slab_pair_q(w, c, 0.001f, t_cull, tl, tr, hl, hr);
+                    ch.x = (int)w[6]; ch.y = (int)w[7];
+                } else {
+                    f4 na, nb, nc;
+                    load_node(sv.nodes, cur, na, nb, nc, ch);
+                    hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, 0.001f, t_cull, tl);
+                    hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, 0.001f, t_cull, tr);
+                }
+                hr = hr && ch.y != CHILD_NONE;
+                if (hl && hr) {
+                    bool swap = tr < tl;
+                    cur = swap ? ch.y : ch.x;
+                    if (sp < SHIM_BVH_STACK) stack[sp++] = swap ? ch.x : ch.y;
+                } else if (hl) {
+                    cur = ch.x;
+                } else if (hr) {
+                    cur = ch.y;
+                } else {
+                    cur = sp > 0 ? stack[--sp] : SHIM_STACK_END;
+                }
+            };
             for (;;) {
                 // (an idle lane has cur == SHIM_STACK_END: cur alone tells the three states apart)
                 const bool at_node = (uint32_t)cur < (uint32_t)SHIM_STACK_END;
@@ -603,42 +643,10 @@ __global__ void __launch_bounds__(THREADS, 1) wf_bvh1_walk() {
                 if (nm == 0u) break;
                 const unsigned pm = __ballot_sync(0xffffffffu, cur < 0);
                 if (__popc(pm) >= SHIM_BVH1_PRIM_BATCH) break;
-                if (at_node) {
-                    i4 ch;
-                    float tl, tr;
-                    bool hl, hr;
-                    if (COUNT) nodes++;
-                    if (QN) {
-                        uint32_t w[8];
-                        if (QN == 1) {
-                            const uint32_t a = q_base + (uint32_t)cur * (uint32_t)sizeof(QNode);
-                            asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
-                            asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+16];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(a));
-                        } else {
-                            asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(sv.qnodes + cur));
-                        }
-                        slab_pair_q(w, c, 0.001f, t_cull, tl, tr, hl, hr);
-                        ch.x = (int)w[6]; ch.y = (int)w[7];
-                    } else {
-                        f4 na, nb, nc;
-                        load_node(sv.nodes, cur, na, nb, nc, ch);
-                        hl = slab(na.x, na.y, na.z, na.w, nb.x, nb.y, c, 0.001f, t_cull, tl);
-                        hr = slab(nb.z, nb.w, nc.x, nc.y, nc.z, nc.w, c, 0.001f, t_cull, tr);
-                    }
-                    hr = hr && ch.y != CHILD_NONE;
-                    if (hl && hr) {
-                        bool swap = tr < tl;
-                        cur = swap ? ch.y : ch.x;
-                        if (sp < SHIM_BVH_STACK) stack[sp++] = swap ? ch.x : ch.y;
-                    } else if (hl) {
-                        cur = ch.x;
-                    } else if (hr) {
-                        cur = ch.y;
-                    } else {
-                        cur = sp > 0 ? stack[--sp] : SHIM_STACK_END;
-                    }
-                }
+                if (at_node) node_step();
+#pragma unroll
+                for (int extra = 1; extra < (QN ? SHIM_BVH1_STEPS_PER_VOTE : 1); ++extra)
+                    if ((uint32_t)cur < (uint32_t)SHIM_STACK_END) node_step();
             }
             // ---- one round of primitive tests (same rules as bvh_closest: closer wins, an exact tie goes to the later leaf)
             if (active && cur < 0) {
